@@ -1,0 +1,3 @@
+from pantea_b200.models.nn.model import NeuralNetworkModel
+
+__all__ = ["NeuralNetworkModel"]

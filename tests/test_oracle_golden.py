@@ -1,0 +1,197 @@
+"""Pins the two oracle tiers to every known answer the reference holds for the hot path
+(tests/golden/reference_vectors.json cites the reference file:line of each vector), then
+checks the analytic C oracle against the faithful dense restatement on other inputs.
+CPU only -- this is the checker being checked, not the product."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, dense_oracle as D
+from oracle.spec import (ElementSpec, SymFuncSpec, load_potential, md_velocities, read_runner, rune_width_potential,
+                         type_map, water_box, water_masses, FROM_ATOMIC_MASS, MASS_U)
+
+
+@pytest.fixture(scope="module")
+def vec(golden_dir):
+    return json.loads((golden_dir / "reference_vectors.json").read_text())
+
+
+@pytest.fixture(scope="module")
+def h2o(golden_dir):
+    f = read_runner(golden_dir / "h2o.data")[0]
+    f["positions"] = np.remainder(f["positions"], f["box"])  # Structure.__post_init__ wrap (structure.py:80-81)
+    return f
+
+
+@pytest.fixture(scope="module")
+def pot(golden_dir):
+    return load_potential(golden_dir / "h2o.json")
+
+
+def _t(a):
+    return torch.as_tensor(np.asarray(a), dtype=torch.float64)
+
+
+def test_ne2_g2_no_pbc(vec):
+    v = vec["ne2_g2"]
+    pos, types = np.asarray(v["positions"]), np.ones(2, dtype=np.int32)
+    spec = ElementSpec(1, [SymFuncSpec(2, v["cutoff"][0], v["cutoff"][1], 1, 0, v["eta"], rs) for rs in v["r_shifts"]])
+    dense = D.acsf_values(D.symfuncs_from_spec(spec), _t(pos), torch.as_tensor(types), None, torch.arange(2))
+    np.testing.assert_allclose(dense.numpy(), np.tile(v["expected_row"], (2, 1)), rtol=1e-8)
+    G, _ = c_oracle.acsf(spec, pos, types, None)
+    np.testing.assert_allclose(G, np.tile(v["expected_row"], (2, 1)), rtol=1e-8)
+
+
+def test_h2o_pbc_g2_g3(vec, h2o):
+    v = vec["h2o_pbc_g2_g3"]
+    tm = type_map(h2o["elements"])
+    ct, rc = v["cutoff"]
+    spec = ElementSpec(tm["O"], [
+        SymFuncSpec(2, ct, rc, tm[v["radial"]["neighbor"]], 0, v["radial"]["eta"], v["radial"]["r_shift"]),
+        SymFuncSpec(3, ct, rc, tm["H"], tm["H"], v["angular"]["eta"], 0.0, v["angular"]["lambda0"], v["angular"]["zeta"]),
+    ])
+    centres = np.nonzero(h2o["types"] == tm["O"])[0]
+    dense = D.acsf_values(D.symfuncs_from_spec(spec), _t(h2o["positions"]), torch.as_tensor(h2o["types"]),
+                          _t(h2o["box"]), torch.as_tensor(centres))
+    assert tuple(dense.shape) == tuple(v["shape"])
+    np.testing.assert_allclose(dense[0].numpy(), v["expected_atom0"], rtol=0, atol=6e-11)  # 10 printed decimals
+    G, _ = c_oracle.acsf(spec, h2o["positions"], h2o["types"], h2o["box"], centres)
+    np.testing.assert_allclose(G[0], v["expected_atom0"], rtol=0, atol=6e-11)
+    np.testing.assert_allclose(G, dense.numpy(), rtol=1e-12, atol=1e-18)
+
+
+def test_notebook_distances_and_neighbors(vec, h2o):
+    d = c_oracle.distances(h2o["positions"], h2o["box"])
+    np.testing.assert_allclose(d[0, :5], vec["notebook_distances"]["expected"], atol=5e-9)
+    r, _ = D.distances_with_aux(_t(h2o["positions"]), _t(h2o["positions"]), _t(h2o["box"]))
+    assert np.array_equal(r.numpy(), d)  # the two tiers agree bit for bit on distances
+    row_ptr, col = c_oracle.neighbors(h2o["positions"], h2o["types"], h2o["box"], vec["notebook_neighbors"]["r_cutoff"])
+    assert row_ptr[1] - row_ptr[0] == vec["notebook_neighbors"]["expected_count_atom0"]
+    mask = D.cutoff_mask(r, vec["notebook_neighbors"]["r_cutoff"]).numpy()
+    for i in range(len(d)):
+        assert np.array_equal(np.nonzero(mask[i])[0], col[row_ptr[i]:row_ptr[i + 1]])
+
+
+def _notebook_spec(v, tm):
+    ct, rc = v["cutoff"]
+    sfs = [SymFuncSpec(2, ct, rc, tm[r["neighbor"]], 0, r["eta"], r["r_shift"]) for r in v["radial"]]
+    sfs += [SymFuncSpec(a["kind"], ct, rc, tm[a["neighbors"][0]], tm[a["neighbors"][1]], a["eta"], 0.0, a["lambda0"],
+                        a["zeta"]) for a in v["angular"]]
+    return ElementSpec(tm["O"], sfs)
+
+
+def test_notebook_acsf_values_and_grad(vec, h2o):
+    v = vec["notebook_acsf"]
+    tm = type_map(h2o["elements"])
+    spec = _notebook_spec(v, tm)
+    centres = np.nonzero(h2o["types"] == tm["O"])[0]
+    args = (D.symfuncs_from_spec(spec), _t(h2o["positions"]), torch.as_tensor(h2o["types"]), _t(h2o["box"]))
+    dense = D.acsf_values(*args, torch.as_tensor(centres)).numpy()
+    np.testing.assert_allclose(dense, v["expected_values"], rtol=2e-8)
+    # ACSF.grad(structure)[:1]: all atoms are centres, first row is atom 0 (acsf.py:103-104)
+    gd = D.acsf_grad(*args, torch.arange(len(h2o["types"]))).numpy()
+    np.testing.assert_allclose(gd[0], v["expected_grad_atom0"], atol=6e-9)
+    G, dG = c_oracle.acsf(spec, h2o["positions"], h2o["types"], h2o["box"], None)
+    np.testing.assert_allclose(G[centres], dense, rtol=1e-12, atol=1e-18)
+    np.testing.assert_allclose(dG, gd, rtol=1e-10, atol=1e-16)
+
+
+def test_nnp_energy_forces_fp32_goldens(vec, h2o, pot):
+    v = vec["nnp_fp32"]
+    e, e_atom, f = D.energy_and_forces(D.models_from_specs(pot), _t(h2o["positions"]), torch.as_tensor(h2o["types"]),
+                                       _t(h2o["box"]))
+    # goldens are float32 results compared with jnp.allclose defaults (rtol 1e-5, atol 1e-8)
+    # E is a sum of 12 atomic energies of magnitude ~0.2 that cancel to -0.0072: the float32 golden carries an
+    # accumulation error of ~12 * 0.2 * 2^-24 ~ 1.5e-7 (a float32 run of this oracle gives -0.00721341)
+    np.testing.assert_allclose(float(e), v["energy"], rtol=0, atol=3e-7)
+    np.testing.assert_allclose(f.numpy(), v["forces"], rtol=1e-5, atol=1e-7)
+    ec, eac, fc = c_oracle.energy_forces(pot, h2o["positions"], h2o["types"], h2o["box"])
+    np.testing.assert_allclose(ec, float(e), rtol=1e-12)
+    np.testing.assert_allclose(eac, e_atom.numpy(), rtol=1e-11, atol=1e-16)
+    np.testing.assert_allclose(fc, f.numpy(), rtol=1e-10, atol=1e-15)
+    # the reference force is the central-role partial derivative: it does not sum to zero
+    assert np.abs(f.numpy().sum(axis=0)).max() > 1e-2
+
+
+def test_masses(vec):
+    for el in ("H", "O", "Ne"):
+        assert MASS_U[el] * FROM_ATOMIC_MASS == pytest.approx(vec["masses"][el], rel=1e-14)
+
+
+@pytest.mark.parametrize("cutoff", ["hard", "cos", "tanhu", "tanh", "exp", "poly1", "poly2"])
+def test_c_vs_dense_all_cutoffs_g9_zeta(cutoff):
+    """Unpinned-by-reference features: every cutoff type, G1, G9, zeta > 1, lambda = -1,
+    mixed cutoff radii -- analytic C gradients against dense autograd."""
+    pos, types, box = water_box(48, seed=11)
+    rc = 0.9 if cutoff in ("poly1", "poly2") else 9.0  # poly* act on raw r: only sensible for r < 1
+    if cutoff in ("poly1", "poly2"):
+        pos, box = pos / 12.0, box / 12.0
+    spec = ElementSpec(2, [
+        SymFuncSpec(1, cutoff, rc, 1), SymFuncSpec(2, cutoff, rc * 0.8, 2, 0, 0.05, 0.5),
+        SymFuncSpec(3, cutoff, rc, 1, 1, 0.01, 0.0, -1.0, 4.0), SymFuncSpec(3, cutoff, rc * 0.9, 1, 2, 0.02, 0.0, 1.0, 2.0),
+        SymFuncSpec(9, cutoff, rc, 2, 2, 0.005, 0.0, 1.0, 1.0), SymFuncSpec(9, cutoff, rc, 2, 1, 0.03, 0.0, -1.0, 3.0),
+        SymFuncSpec(3, cutoff, rc, 2, 2, 0.03, 0.0, 1.0, 2.5),
+    ])
+    args = (D.symfuncs_from_spec(spec), _t(pos), torch.as_tensor(types), _t(box))
+    centres = torch.arange(len(types))
+    gd, dgd = D.acsf_values(*args, centres).numpy(), D.acsf_grad(*args, centres).numpy()
+    G, dG = c_oracle.acsf(spec, pos, types, box)
+    scale = np.abs(gd).max(axis=0) + 1e-300
+    assert np.abs((G - gd) / scale).max() < 1e-12
+    gscale = np.abs(dgd).max(axis=(0, 2))[None, :, None] + 1e-300
+    assert np.abs((dG - dgd) / gscale).max() < 1e-11
+
+
+@pytest.mark.parametrize("scale_type", ["center", "scale", "scale_center", "scale_center_sigma"])
+def test_c_vs_dense_energy_forces_water96(scale_type, pot):
+    pos, types, box = water_box(96, seed=5)
+    specs = [ElementSpec(s.atom_type, s.symfuncs, scale_type, s.scaler, 0.0, 1.0, s.layers) for s in pot]
+    e, e_atom, f = D.energy_and_forces(D.models_from_specs(specs), _t(pos), torch.as_tensor(types), _t(box))
+    ec, eac, fc = c_oracle.energy_forces(specs, pos, types, box)
+    np.testing.assert_allclose(eac, e_atom.numpy(), rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(fc, f.numpy(), rtol=1e-9, atol=1e-13)
+    assert abs(ec - float(e)) < 1e-12 * max(1.0, abs(float(e)))
+
+
+def test_c_vs_dense_wide_potential_and_activations():
+    pos, types, box = water_box(48, seed=3)
+    specs = rune_width_potential()
+    acts = ["logistic", "softplus", "gaussian", "cos", "exp", "harmonic", "relu", "tanh"]
+    for i, s in enumerate(specs):
+        s.layers = [(k, b, acts[(2 * i + l) % len(acts)] if l < 2 else "identity") for l, (k, b, _) in enumerate(s.layers)]
+    e, e_atom, f = D.energy_and_forces(D.models_from_specs(specs), _t(pos), torch.as_tensor(types), _t(box))
+    ec, eac, fc = c_oracle.energy_forces(specs, pos, types, box)
+    np.testing.assert_allclose(eac, e_atom.numpy(), rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(fc, f.numpy(), rtol=1e-9, atol=1e-12)
+
+
+def test_no_box_structure(pot):
+    pos, types, _ = water_box(24, seed=9)
+    e, e_atom, f = D.energy_and_forces(D.models_from_specs(pot), _t(pos), torch.as_tensor(types), None)
+    ec, eac, fc = c_oracle.energy_forces(pot, pos, types, None)
+    np.testing.assert_allclose(eac, e_atom.numpy(), rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(fc, f.numpy(), rtol=1e-9, atol=1e-13)
+
+
+def test_md_c_oracle_matches_dense_steps(pot):
+    """Velocity Verlet without mass + Berendsen (molecular_dynamics.py:16-77, thermostat.py:12-22)."""
+    pos, types, box = water_box(24, seed=2)
+    vel = md_velocities(types)
+    mass = water_masses(types)
+    dt, tau, t0, kb = 0.25, 25.0, 300.0, 3.166811563e-6
+    p1, v1, f1, sc = c_oracle.md_run(pot, pos, vel, mass, types, box, dt, 3, t0, tau, kb)
+    models = D.models_from_specs(pot)
+    x, v, m = _t(pos), _t(vel), _t(mass)[:, None]
+    tb, ty = _t(box), torch.as_tensor(types)
+    _, _, f = D.energy_and_forces(models, x, ty, tb)
+    for _ in range(3):
+        x = D.wrap_into_box(D.verlet_positions(x, v, f, dt), tb)
+        _, _, fn = D.energy_and_forces(models, x, ty, tb)
+        v = D.verlet_velocities(v, f, fn, dt)
+        f = fn
+        v = D.berendsen_scale(v, dt, tau, D.temperature(v, m, kb), t0)
+    np.testing.assert_allclose(p1, x.numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(v1, v.numpy(), rtol=1e-10, atol=1e-14)
+    assert sc.shape == (4, 3) and np.isfinite(sc).all()
