@@ -1,0 +1,201 @@
+/*
+ * pantea_b200 -- C ABI of the B200-native HDNNP energy/force hot path.
+ *
+ * The reference (hghcomphys/pantea, Python/JAX) has no FFI layer: its "operator interface" for
+ * this path is the set of module-level jitted kernels that take plain arrays.  Every entry
+ * point below replaces one of them (reference file:line given per function, paths relative to
+ * the pantea repository) and is what a binding on the reference side (ctypes, or an XLA FFI
+ * custom-call wrapping the same symbols -- see INTEGRATION.md) would bind.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Unless stated otherwise pointers are DEVICE pointers
+ *     (borrowed, never freed or resized here); descriptors (`*_desc`) and `box` are HOST memory.
+ *   - `dtype` is PANTEA_F64 or PANTEA_F32 and selects the arithmetic and the element type of
+ *     every `void*` array of that workspace (reference: `default_dtype.FLOATX`, types.py:13-30).
+ *   - Atom types are 1-based and ordered by ascending atomic number among the potential's
+ *     elements (reference element.py:99-108).  Types outside 1..n_elements are legal atoms that
+ *     no symmetry function refers to.
+ *   - All functions are asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant per
+ *     workspace handle, and return 0 on success or a negative PANTEA_E* code; the message is
+ *     available from pantea_last_error() (thread local).  Device-side capacity overflow is
+ *     reported by pantea_neighbor_status().
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     PANTEA_ECUDA.
+ */
+#ifndef PANTEA_B200_H
+#define PANTEA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PANTEA_OK 0
+#define PANTEA_EINVAL (-1)
+#define PANTEA_ECUDA (-2)
+#define PANTEA_ECAPACITY (-3)
+#define PANTEA_ENOMEM (-4)
+
+#define PANTEA_F64 64
+#define PANTEA_F32 32
+
+#define PANTEA_MAX_TYPES 8       /* elements per potential */
+#define PANTEA_MAX_SYMFUNC 128   /* symmetry functions per element */
+#define PANTEA_MAX_LAYERS 8      /* dense layers per element network */
+#define PANTEA_MAX_CUTOFFS 4     /* distinct (cutoff type, radius) pairs per element */
+
+/* symmetry function kinds (RuNNer numbering; reference potential.py:213-252) */
+#define PANTEA_G1 1
+#define PANTEA_G2 2
+#define PANTEA_G3 3
+#define PANTEA_G9 9
+
+/* cutoff function types (RuNNer `cutoff_type`; reference settings.py:43-51, cutoff.py:45-110) */
+enum { PANTEA_CUT_HARD = 0, PANTEA_CUT_COS = 1, PANTEA_CUT_TANHU = 2, PANTEA_CUT_TANH = 3,
+       PANTEA_CUT_EXP = 4, PANTEA_CUT_POLY1 = 5, PANTEA_CUT_POLY2 = 6 };
+
+/* activation functions (reference activation.py:48-60; EXP is exp(-x)) */
+enum { PANTEA_ACT_IDENTITY = 0, PANTEA_ACT_TANH = 1, PANTEA_ACT_LOGISTIC = 2, PANTEA_ACT_SOFTPLUS = 3,
+       PANTEA_ACT_RELU = 4, PANTEA_ACT_GAUSSIAN = 5, PANTEA_ACT_COS = 6, PANTEA_ACT_EXP = 7,
+       PANTEA_ACT_HARMONIC = 8 };
+
+/* force definitions */
+#define PANTEA_FORCE_REFERENCE 0 /* -dE_i/dr_i in the central role only == reference force.py:16-43 */
+
+typedef struct pantea_symfunc_desc {
+    int32_t kind;        /* PANTEA_G1 / G2 / G3 / G9 */
+    int32_t cutoff_type; /* PANTEA_CUT_* */
+    int32_t type_j;      /* neighbour atom type (1-based) */
+    int32_t type_k;      /* second neighbour type for G3/G9, 0 otherwise */
+    double r_cutoff;
+    double eta;
+    double r_shift;      /* used by G2 only (G3/G9 ignore it, reference angular.py:58-65,100-107) */
+    double lambda0;
+    double zeta;
+} pantea_symfunc_desc;
+
+typedef struct pantea_element_desc {
+    int32_t n_symfunc;                  /* radial functions first, then angular: output column order */
+    const pantea_symfunc_desc* symfunc;
+    /* scaler as x' = offset + slope * (x - shift) per feature; all NULL = identity
+       (reference scaler.py:206-246 expressed as an affine map) */
+    const double* scale_shift;
+    const double* scale_slope;
+    const double* scale_offset;
+    /* network: n_layers dense layers, layer_sizes[n_layers+1] with layer_sizes[0] == n_symfunc,
+       activations[n_layers], weights packed per layer as kernel [in,out] row-major then bias [out]
+       (reference model.py:40-58; tests/test_nn.py:97-138 for the layout).  n_layers == 0: descriptor only. */
+    int32_t n_layers;
+    const int32_t* layer_sizes;
+    const int32_t* activations;
+    const double* weights;
+} pantea_element_desc;
+
+typedef struct pantea_potential_desc {
+    int32_t n_elements;                  /* element e describes atom type e+1 */
+    const pantea_element_desc* elements;
+} pantea_potential_desc;
+
+typedef struct pantea_potential pantea_potential;
+typedef struct pantea_workspace pantea_workspace;
+
+const char* pantea_last_error(void);
+const char* pantea_version(void);
+/* number of visible CUDA devices (0 when none / driver missing); never fails */
+int pantea_device_count(void);
+
+/* -- potential: replaces the static `atomic_potentials` pytree + params handed to the jitted kernels
+      (reference potential.py:47-65, 140-317; energy.py:45-66).  Host descriptors are copied. */
+int pantea_potential_create(const pantea_potential_desc* desc, pantea_potential** out);
+int pantea_potential_destroy(pantea_potential* pot);
+double pantea_potential_cutoff(const pantea_potential* pot); /* max r_cutoff (potential.py:374-382) */
+
+/* -- workspace: library-owned scratch (cell list, neighbour rows, packed atom records) for up to
+      `max_atoms` atoms and `max_neighbors` neighbours per atom.  `pot` may be NULL for a pure
+      neighbour-search workspace. */
+int pantea_workspace_create(const pantea_potential* pot, int64_t max_atoms, int32_t max_neighbors, int32_t dtype,
+                            pantea_workspace** out);
+int pantea_workspace_destroy(pantea_workspace* ws);
+
+/* -- neighbour search: replaces `_calculate_cutoff_masks*` / `_calculate_distances*`
+      (reference neighbor.py:74-115, distance.py:63-105, box.py:112-117).
+      Neighbour <=> 0 < r <= r_cutoff with r = sqrt((dx^2+dy^2)+dz^2) of the single-shift minimum image
+      d = r_i - r_j.  `box` = HOST double[3] lattice diagonal, or NULL for an open (non-periodic) structure.
+      A periodic cell list is used when the box holds >= 3 cells of width >= r_cutoff per dimension,
+      otherwise all pairs are scanned (exactly one image per pair, as the reference).
+      Binds `positions`/`types` (snapshot) to the workspace for the calls below. */
+int pantea_neighbor_build(pantea_workspace* ws, const void* positions /*[n,3]*/, const int32_t* types /*[n]*/,
+                          int64_t n_atoms, const double* box, double r_cutoff, void* stream);
+/* many independent structures in one launch (dataset preprocessing): atoms of structure s are
+   [struct_ptr[s], struct_ptr[s+1]); boxes = DEVICE double [n_structs,3] or NULL. */
+int pantea_neighbor_build_batch(pantea_workspace* ws, const void* positions, const int32_t* types, int64_t n_atoms,
+                                const int32_t* struct_ptr /*[n_structs+1]*/, const double* boxes, int64_t n_structs,
+                                double r_cutoff, void* stream);
+/* restrict subsequent row building / energy evaluation to atoms [begin,end) (multi-GPU ownership) */
+int pantea_workspace_set_owned_range(pantea_workspace* ws, int64_t begin, int64_t end);
+/* synchronises `stream`; returns PANTEA_ECAPACITY if a row overflowed max_neighbors.  *max_count (HOST,
+   may be NULL) receives the largest neighbour count seen. */
+int pantea_neighbor_status(pantea_workspace* ws, int32_t* max_count, void* stream);
+int pantea_neighbor_counts(pantea_workspace* ws, int32_t* counts /*[n]*/, void* stream);
+/* CSR export with columns ascending within a row; row_ptr = exclusive prefix sum of the counts */
+int pantea_neighbor_export(pantea_workspace* ws, const int64_t* row_ptr /*[n+1]*/, int32_t* col_idx, void* stream);
+/* dense minimum-image distances (and optionally d = r_i - r_j) between two index subsets of the bound
+   structure; NULL index = all atoms.  Replaces `calculate_distances` (reference distance.py:17-60). */
+int pantea_distances(pantea_workspace* ws, const int32_t* idx_i, int64_t n_i, const int32_t* idx_j, int64_t n_j,
+                     void* r /*[n_i,n_j]*/, void* d /*[n_i,n_j,3] or NULL*/, void* stream);
+
+/* -- descriptor: replaces `_jitted_calculate_acsf_descriptor` and `_jitted_calculate_grad_acsf_descriptor`
+      (reference acsf.py:163-228).  Applies the symmetry functions of element `element` (0-based slot) to the
+      centres `centres[n_centres]` (atom indices of the bound structure, any type; NULL = all atoms).
+      G [n_centres, n_symfunc]; dG [n_centres, n_symfunc, 3] = dG_i/dr_i in the central role, or NULL. */
+int pantea_acsf_compute(pantea_workspace* ws, int32_t element, const int32_t* centres, int64_t n_centres, void* G,
+                        void* dG, void* stream);
+
+/* -- energy and forces: replaces `_jitted_compute_energy` and `_jitted_grad_compute_energy`
+      (reference energy.py:45-66, force.py:16-43, potential.py:67-102).  One fused launch per call:
+      symmetry functions + central gradients -> scaler -> per-element network forward/backward ->
+      F_i = -sum_s dE_i/dG_is dG_is/dr_i.  e_atom [n] / forces [n,3] / e_total [1] may each be NULL.
+      Only the owned range is written; e_total sums the owned atoms (deterministic order). */
+int pantea_energy_forces(pantea_workspace* ws, void* e_atom, void* forces, void* e_total, int32_t force_mode,
+                         void* stream);
+
+/* -- molecular dynamics pieces: replace `_get_verlet_new_positions/_velocities`, `_wrap_into_box`,
+      `_get_kinetic_energy`, `_get_rescaled_velocities` (reference molecular_dynamics.py:16-30, box.py:123-126,
+      system.py:20-29, thermostat.py:12-22).  No mass enters the integrator (as the reference).
+      All act on atoms [begin,end). */
+int pantea_md_update_positions(void* positions, const void* velocities, const void* forces, int64_t begin,
+                               int64_t end, const double* box, double dt, int32_t dtype, void* stream);
+int pantea_md_update_velocities(void* velocities, void* forces /*in: F(t), out: F(t+dt)*/, const void* new_forces,
+                                int64_t begin, int64_t end, double dt, int32_t dtype, void* stream);
+/* ke_out: DEVICE double[1] = 0.5 * sum m v^2 over [begin,end) (fixed-order reduction) */
+int pantea_md_kinetic_energy(const void* velocities, const void* masses, int64_t begin, int64_t end, double* ke_out,
+                             int32_t dtype, void* stream);
+/* Berendsen: v *= 1/sqrt(1 + dt/tau (T/T0 - 1)), T = 2 KE / (3 n_total kB), KE read from DEVICE ke[0] */
+int pantea_md_rescale_velocities(void* velocities, int64_t begin, int64_t end, const double* ke, int64_t n_total,
+                                 double dt, double tau, double t_target, double kb, int32_t dtype, void* stream);
+
+typedef struct pantea_md_params {
+    double dt;
+    double t_target;  /* Berendsen target temperature [K]; ignored when tau <= 0 */
+    double tau;       /* Berendsen time constant; <= 0 disables the thermostat */
+    double kb;        /* Boltzmann constant in the caller's units */
+    int32_t record;   /* != 0: write (E_pot, E_kin) of every step into `scalars` */
+    int32_t use_graph;/* != 0: replay the step as a CUDA graph */
+} pantea_md_params;
+
+/* Runs n_steps velocity-Verlet steps entirely on the device, no host synchronisation inside:
+   replaces the `simulate` -> `MDSimulator.simulate_one_step` loop (reference simulate.py:77-83,
+   molecular_dynamics.py:57-77).  forces must hold F(positions) on entry.  scalars: DEVICE double
+   [n_steps, 2] (E_pot, E_kin after each step) when params->record, else may be NULL. */
+int pantea_md_run(pantea_workspace* ws, void* positions, void* velocities, void* forces, const void* masses,
+                  const int32_t* types, int64_t n_atoms, const double* box, int64_t n_steps,
+                  const pantea_md_params* params, double* scalars, void* stream);
+
+/* counters for bench.py: number of kernel launches issued through this library since load */
+int64_t pantea_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANTEA_B200_H */

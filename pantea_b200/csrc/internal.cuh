@@ -1,0 +1,199 @@
+// Internal declarations shared by the translation units of libpantea_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "pantea_b200.h"
+
+namespace pantea {
+
+// ------------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+void count_launch(int n = 1);
+int64_t launch_count();
+
+#define PANTEA_CUDA_TRY(expr)                                                                         \
+    do {                                                                                              \
+        cudaError_t err__ = (expr);                                                                   \
+        if (err__ != cudaSuccess)                                                                     \
+            return ::pantea::fail(PANTEA_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
+    } while (0)
+
+#define PANTEA_LAUNCH_CHECK()                                                                         \
+    do {                                                                                              \
+        cudaError_t err__ = cudaGetLastError();                                                       \
+        if (err__ != cudaSuccess)                                                                     \
+            return ::pantea::fail(PANTEA_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(err__)); \
+        ::pantea::count_launch();                                                                     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device-side potential tables (parameters kept in double; kernels convert to their arithmetic type)
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxTypes = PANTEA_MAX_TYPES;
+constexpr int kMaxSF = PANTEA_MAX_SYMFUNC;
+constexpr int kMaxLayers = PANTEA_MAX_LAYERS;
+constexpr int kMaxCut = PANTEA_MAX_CUTOFFS;
+constexpr int kMaxGroups = 64;
+constexpr int kBuckets = kMaxTypes + 1;  // neighbour rows are partitioned by type; last bucket = "other"
+
+struct RadialSF {
+    int type_j;  // 0-based bucket
+    int kind;    // 1 | 2
+    int cls;     // cutoff class
+    int out;     // output column
+    double eta, r_shift;
+};
+
+struct AngularMember {
+    double eta, lambda0, zeta, pref;  // pref = 2^(1-zeta)
+    int izeta;                        // zeta when it is a small non-negative integer, else -1
+    int out;
+};
+
+struct AngularGroup {
+    int type_j, type_k;  // 0-based buckets
+    int cls;
+    int kind;  // 3 | 9
+    int first, count;  // members [first, first+count)
+};
+
+struct CutoffClass {
+    int type;
+    double rc;
+};
+
+struct ElementTable {
+    int n_sf, n_radial, n_groups, n_cls;
+    double rc_max;
+    CutoffClass cls[kMaxCut];
+    RadialSF radial[kMaxSF];
+    AngularGroup groups[kMaxGroups];
+    AngularMember members[kMaxSF];
+    int has_scaler;
+    double shift[kMaxSF], slope[kMaxSF], offset[kMaxSF];
+    int n_layers;
+    int sizes[kMaxLayers + 1];
+    int acts[kMaxLayers];
+    int w_off[kMaxLayers];  // offset of the layer's kernel in `weights` (bias follows the kernel)
+    int n_neurons;          // sum of sizes[1..]
+    const double* weights;  // device
+};
+
+}  // namespace pantea
+
+struct pantea_potential {
+    int n_elements = 0;
+    double rc_max = 0.0;
+    int max_sf = 0, max_cls = 1, max_neurons = 0, max_width = 0;
+    std::vector<pantea::ElementTable> host;
+    pantea::ElementTable* dev = nullptr;  // [n_elements]
+    std::vector<double*> dev_weights;
+};
+
+namespace pantea {
+
+// packed atom record in cell-sorted order
+template <typename T>
+struct Rec;
+template <>
+struct __align__(16) Rec<double> {
+    double x, y, z;
+    int type;  // 0-based bucket
+    int idx;   // original atom index
+};
+template <>
+struct __align__(16) Rec<float> {
+    float x, y, z;
+    int tidx;  // bucket << 28 | original index
+};
+
+template <typename T>
+__host__ __device__ inline int rec_type(const Rec<T>& r);
+template <>
+__host__ __device__ inline int rec_type<double>(const Rec<double>& r) { return r.type; }
+template <>
+__host__ __device__ inline int rec_type<float>(const Rec<float>& r) { return (int)((unsigned)r.tidx >> 28); }
+template <typename T>
+__host__ __device__ inline int rec_idx(const Rec<T>& r);
+template <>
+__host__ __device__ inline int rec_idx<double>(const Rec<double>& r) { return r.idx; }
+template <>
+__host__ __device__ inline int rec_idx<float>(const Rec<float>& r) { return r.tidx & 0x0fffffff; }
+__host__ __device__ inline void rec_set(Rec<double>& r, int type, int idx) { r.type = type; r.idx = idx; }
+__host__ __device__ inline void rec_set(Rec<float>& r, int type, int idx) { r.tidx = (int)(((unsigned)type << 28) | (unsigned)idx); }
+
+enum NeighborMode { kModeNone = 0, kModeCell = 1, kModeAllPairs = 2 };
+
+}  // namespace pantea
+
+struct pantea_workspace {
+    const pantea_potential* pot = nullptr;
+    int64_t max_atoms = 0;
+    int cap = 0;    // neighbours per row
+    int dtype = PANTEA_F64;
+    int n_types = 0;  // buckets used by the potential (others -> bucket n_types)
+
+    // current binding
+    int64_t n = 0;
+    int mode = pantea::kModeNone;
+    bool has_box = false;
+    double box[3] = {0, 0, 0};
+    double rc = 0.0;
+    int ncell[3] = {1, 1, 1};
+    int64_t n_structs = 0;
+    const int32_t* struct_ptr = nullptr;  // borrowed (batch mode)
+    const double* boxes = nullptr;        // borrowed (batch mode)
+    int64_t own_begin = 0, own_end = -1;  // -1: all atoms
+
+    // device buffers
+    void* rec = nullptr;           // Rec<T>[max_atoms]
+    int32_t* slot_of = nullptr;    // [max_atoms] original index -> sorted slot
+    int32_t* struct_of = nullptr;  // [max_atoms] structure id per sorted slot (batch mode)
+    int32_t* nbr = nullptr;        // [max_atoms * cap] sorted-slot indices, partitioned by bucket
+    int32_t* nbr_tcount = nullptr; // [max_atoms * kBuckets]
+    int32_t* cell_of = nullptr;    // [max_atoms]
+    int32_t* tmp_order = nullptr;  // [max_atoms]
+    int32_t* cell_start = nullptr; // [cell_cap + 1]
+    int32_t* cell_fill = nullptr;  // [cell_cap]
+    int64_t cell_cap = 0;
+    int32_t* flags = nullptr;      // [4]: max neighbour count seen, ...
+    double* e_partial = nullptr;   // reduction scratch
+    int64_t e_partial_cap = 0;
+    void* md_forces = nullptr;     // [max_atoms,3] F(t+dt) scratch for pantea_md_run
+    double* md_ke = nullptr;       // [1]
+    void* md_eatom = nullptr;      // [max_atoms]
+    cudaGraphExec_t md_graph = nullptr;
+    cudaStream_t capture_stream = nullptr;
+    int md_graph_nodes = 0;        // kernel launches per replay
+    // key of the captured graph
+    struct GraphKey {
+        const void *pos = nullptr, *vel = nullptr, *frc = nullptr, *mass = nullptr, *types = nullptr, *scalars = nullptr;
+        int64_t n = 0;
+        double dt = 0, tau = 0, t0 = 0, kb = 0, box[3] = {0, 0, 0};
+        int record = 0, has_box = 0;
+        bool operator==(const GraphKey& o) const {
+            return pos == o.pos && vel == o.vel && frc == o.frc && mass == o.mass && types == o.types &&
+                   scalars == o.scalars && n == o.n && dt == o.dt && tau == o.tau && t0 == o.t0 && kb == o.kb &&
+                   box[0] == o.box[0] && box[1] == o.box[1] && box[2] == o.box[2] && record == o.record &&
+                   has_box == o.has_box;
+        }
+    } md_key;
+};
+
+namespace pantea {
+// implemented in neighbor.cu
+int neighbor_build_impl(pantea_workspace* ws, const void* pos, const int32_t* types, int64_t n, const double* box,
+                        const int32_t* struct_ptr, const double* boxes, int64_t n_structs, double rc, cudaStream_t st);
+// implemented in acsf.cu
+int atom_kernel_launch(pantea_workspace* ws, int element_slot, const int32_t* centres, int64_t n_centres, void* G,
+                       void* dG, void* e_atom, void* forces, cudaStream_t st);
+int reduce_energy(pantea_workspace* ws, const void* e_atom, void* e_total, cudaStream_t st);
+int ensure_cell_capacity(pantea_workspace* ws, int64_t ncells);
+}  // namespace pantea

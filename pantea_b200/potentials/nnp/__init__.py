@@ -1,0 +1,5 @@
+from pantea_b200.potentials.nnp.atomic_potential import AtomicPotential
+from pantea_b200.potentials.nnp.potential import NNP, NeuralNetworkPotential
+from pantea_b200.potentials.nnp.settings import NeuralNetworkPotentialSettings
+
+__all__ = ["AtomicPotential", "NeuralNetworkPotential", "NNP", "NeuralNetworkPotentialSettings"]

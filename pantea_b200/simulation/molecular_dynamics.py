@@ -1,0 +1,105 @@
+"""Velocity-Verlet MD driver (API of reference `pantea/simulation/molecular_dynamics.py:33-90`).
+
+As in the reference no mass enters the integrator: x += v dt + F dt^2 / 2, v += (F + F') dt / 2
+(`molecular_dynamics.py:16-30`), positions are wrapped after the drift, and the Berendsen
+thermostat acts after the step with the post-step temperature (`:57-63`).
+
+`simulate_one_step` follows the reference call by call through the C ABI.  `simulate_steps` runs
+many steps in a single `pantea_md_run` call -- neighbour build, fused force kernel and integrator
+replayed as one CUDA graph per step with no host synchronisation -- when the potential is a
+`NeuralNetworkPotential`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from pantea_b200 import _lib, engine
+from pantea_b200.simulation.system import System
+from pantea_b200.simulation.thermostat import BrendsenThermostat
+from pantea_b200.units import units
+
+
+class MDSimulator:
+    def __init__(self, time_step: float, thermostat: Optional[BrendsenThermostat] = None) -> None:
+        self.time_step: float = float(time_step)
+        self.thermostat = thermostat
+        self.step: int = 0
+        self.elapsed_time: float = 0.0
+
+    def simulate_one_step(self, system: System) -> None:
+        self.verlet_integration(system)
+        self.step += 1
+        self.elapsed_time += float(self.time_step)
+        if self.thermostat is not None:
+            system.velocities = self.thermostat.get_rescaled_velocities(self, system)
+
+    def verlet_integration(self, system: System) -> None:
+        lib = _lib.load()
+        s = system.structure
+        n = s.natoms
+        code = _lib.dtype_code(s.dtype)
+        pos = s.positions.clone().contiguous()
+        vel = system.velocities.clone().contiguous()
+        frc = s.forces.clone().contiguous()
+        _lib.check(lib.pantea_md_update_positions(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(frc), 0, n,
+                                                  _lib.box_arg(engine.box_lengths(s)), self.time_step, code,
+                                                  _lib.stream_ptr()))
+        s.positions = pos
+        new_forces = system.potential.compute_forces(s).contiguous()
+        _lib.check(lib.pantea_md_update_velocities(_lib.ptr(vel), _lib.ptr(frc), _lib.ptr(new_forces), 0, n,
+                                                   self.time_step, code, _lib.stream_ptr()))
+        system.velocities = vel
+        s.forces = frc  # == new_forces (the kernel rotates F(t+dt) into place)
+
+    # ------------------------------------------------------------------ device-resident loop
+    def simulate_steps(self, system: System, num_steps: int, record: bool = False, use_graph: bool = True):
+        """Run `num_steps` steps on the device.  Returns a [num_steps, 2] tensor of (E_pot, E_kin) when `record`."""
+        potential = system.potential
+        if not hasattr(potential, "device_potential"):
+            for _ in range(num_steps):
+                self.simulate_one_step(system)
+            return None
+        if num_steps <= 0:
+            return None
+        potential._check_scaler_params_exist()
+        s = system.structure
+        dev = potential.device_potential()
+        ws = dev.workspace(s.natoms, s.dtype, engine.number_density(s))
+        types = engine.remap_types(s, dev.type_of).contiguous()
+        box = engine.box_lengths(s)
+        # capacity check once up front (the loop itself never synchronises)
+        ws.bind(s.positions, types, box, dev.r_cutoff)
+        pos = s.positions.clone().contiguous()
+        vel = system.velocities.clone().contiguous()
+        frc = s.forces.clone().contiguous()
+        mass = system.masses.reshape(-1).to(s.dtype).contiguous()
+        scalars = torch.zeros((num_steps, 2), dtype=torch.float64, device=pos.device) if record else None
+        thermo = self.thermostat
+        params = _lib.MDParams(self.time_step, thermo.target_temperature if thermo else 0.0,
+                               thermo.time_constant if thermo else 0.0, units.BOLTZMANN_CONSTANT,
+                               1 if record else 0, 1 if use_graph else 0)
+        _lib.check(_lib.load().pantea_md_run(ws.handle, _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(frc), _lib.ptr(mass),
+                                             _lib.ptr(types), s.natoms, _lib.box_arg(box), int(num_steps),
+                                             C.byref(params), _lib.ptr(scalars), _lib.stream_ptr()))
+        ws._keep = (pos, types)
+        mx = C.c_int32(0)
+        _lib.check(_lib.load().pantea_neighbor_status(ws.handle, C.byref(mx), _lib.stream_ptr()))
+        s.positions, system.velocities, s.forces = pos, vel, frc
+        self.step += num_steps
+        self.elapsed_time += num_steps * float(self.time_step)
+        return scalars
+
+    def repr_physical_params(self, system: System) -> str:
+        if not system.structure.box:
+            return ""
+        return (
+            f"{self.step:<10} "
+            f"time[ps]:{units.TO_PICO_SECOND * self.elapsed_time:<10.5f} "
+            f"Temp[K]:{float(system.get_temperature()):<10.5f} "
+            f"Etot[Ha]:{float(system.get_total_energy()):<15.10f} "
+            f"Epot[Ha]:{float(system.get_potential_energy()):<15.10f} "
+            f"Pres[kb]:{float(system.get_pressure()) * units.TO_KILO_BAR:<10.5f}"
+        )

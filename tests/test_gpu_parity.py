@@ -1,0 +1,281 @@
+"""Parity tests proper: CUDA path (through the C ABI) against the oracle on the same inputs.
+
+Tolerances: neighbour sets bit-exact; descriptors, gradients, energies, forces within 1e-10
+relative in FP64 mode and 1e-5 in FP32 mode (BASELINE.json north_star).  "Relative" is measured
+against the largest magnitude of the compared quantity (per symmetry-function column for
+descriptors), which is how a force/descriptor array is meaningfully compared.
+"""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from oracle.spec import (ElementSpec, SymFuncSpec, load_potential, md_velocities, read_runner, rune_width_potential,
+                         type_map, water_box, water_masses, KB)
+from tests.helpers import csr_rows, cuda, device_potential_from_specs, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP64_TOL = 1e-10
+FP32_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def vec(golden_dir):
+    return json.loads((golden_dir / "reference_vectors.json").read_text())
+
+
+@pytest.fixture(scope="module")
+def pot(golden_dir):
+    return load_potential(golden_dir / "h2o.json")
+
+
+@pytest.fixture(scope="module")
+def h2o(golden_dir):
+    f = read_runner(golden_dir / "h2o.data")[0]
+    f["positions"] = np.remainder(f["positions"], f["box"])
+    return f
+
+
+def _workspace(dev_pot, n, dtype=torch.float64, cap=None):
+    from pantea_b200 import engine
+    return engine.Workspace(dev_pot, max(n, 64), cap or min(max(n - 1, 32), 400), dtype)
+
+
+# ------------------------------------------------------------------------------------------ neighbours
+@pytest.mark.parametrize("n_atoms,rc,use_box", [(12, 12.0, True), (192, 12.0, True), (3000, 12.0, True),
+                                               (3000, 6.5, True), (648, 9.0, False), (6000, 12.0, True)])
+def test_neighbor_sets_bit_exact(n_atoms, rc, use_box, h2o):
+    if n_atoms == 12:
+        pos, types, box = h2o["positions"], h2o["types"], h2o["box"]
+    else:
+        pos, types, box = water_box(n_atoms)
+    box_arg = box if use_box else None
+    row_ptr_o, col_o = c_oracle.neighbors(pos, types, box_arg, rc)
+    ws = _workspace(None, n_atoms)
+    ws.bind(cuda(pos), cuda(types, torch.int32), box_arg, rc)
+    row_ptr, col = ws.neighbor_lists()
+    assert np.array_equal(row_ptr.cpu().numpy(), row_ptr_o)
+    assert np.array_equal(col.cpu().numpy(), col_o)
+
+
+def test_neighbor_capacity_overflow_is_reported_and_grown():
+    from pantea_b200 import _lib, engine
+    pos, types, box = water_box(192)
+    ws = engine.Workspace(None, 192, 32, torch.float64)
+    with pytest.raises(_lib.CapacityError):
+        ws.bind(cuda(pos), cuda(types, torch.int32), box, 12.0, check=False)
+        import ctypes as C
+        _lib.check(_lib.load().pantea_neighbor_status(ws.handle, C.byref(C.c_int32(0)), _lib.stream_ptr()))
+    ws.bind(cuda(pos), cuda(types, torch.int32), box, 12.0)  # grows and succeeds
+    row_ptr_o, col_o = c_oracle.neighbors(pos, types, box, 12.0)
+    row_ptr, col = ws.neighbor_lists()
+    assert np.array_equal(col.cpu().numpy(), col_o)
+
+
+def test_distances_match_oracle(h2o, vec):
+    ws = _workspace(None, 12)
+    ws.bind(cuda(h2o["positions"]), cuda(h2o["types"], torch.int32), h2o["box"], 1e-6, check=False)
+    r, d = ws.distances(None, None, True)
+    assert np.array_equal(r.cpu().numpy(), c_oracle.distances(h2o["positions"], h2o["box"]))
+    np.testing.assert_allclose(r[0, :5].cpu().numpy(), vec["notebook_distances"]["expected"], atol=5e-9)
+    assert d.shape == (12, 12, 3)
+
+
+# ------------------------------------------------------------------------------------------ descriptors
+def _acsf_gpu(spec, pos, types, box, centres=None, dtype=torch.float64):
+    dev = device_potential_from_specs([spec])
+    ws = _workspace(dev, len(pos), dtype)
+    rc = max(s.r_cutoff for s in spec.symfuncs)
+    ws.bind(cuda(pos, dtype), cuda(types, torch.int32), box, rc)
+    c = None if centres is None else cuda(centres, torch.int32)
+    G, dG = ws.acsf(spec.atom_type - 1, len(spec.symfuncs), c, True, True)
+    return G.cpu().numpy(), dG.cpu().numpy()
+
+
+def _assert_descriptor_close(G, dG, G_o, dG_o, tol):
+    col_scale = np.abs(G_o).max(axis=0) + 1e-300
+    assert np.abs((G - G_o) / col_scale).max() < tol
+    g_scale = np.abs(dG_o).max(axis=(0, 2))[None, :, None] + 1e-300
+    assert np.abs((dG - dG_o) / g_scale).max() < tol
+
+
+def test_acsf_golden_vectors(vec, h2o):
+    tm = type_map(h2o["elements"])
+    v = vec["h2o_pbc_g2_g3"]
+    ct, rc = v["cutoff"]
+    spec = ElementSpec(tm["O"], [
+        SymFuncSpec(2, ct, rc, tm["H"], 0, v["radial"]["eta"], v["radial"]["r_shift"]),
+        SymFuncSpec(3, ct, rc, tm["H"], tm["H"], v["angular"]["eta"], 0.0, v["angular"]["lambda0"], v["angular"]["zeta"])])
+    centres = np.nonzero(h2o["types"] == tm["O"])[0]
+    G, _ = _acsf_gpu(spec, h2o["positions"], h2o["types"], h2o["box"], centres)
+    assert G.shape == tuple(v["shape"])
+    np.testing.assert_allclose(G[0], v["expected_atom0"], rtol=0, atol=6e-11)
+    # notebook: values for O atoms and gradient row of atom 0 (all atoms are centres for grad)
+    v = vec["notebook_acsf"]
+    ct, rc = v["cutoff"]
+    sfs = [SymFuncSpec(2, ct, rc, tm[r["neighbor"]], 0, r["eta"], r["r_shift"]) for r in v["radial"]]
+    sfs += [SymFuncSpec(a["kind"], ct, rc, tm[a["neighbors"][0]], tm[a["neighbors"][1]], a["eta"], 0.0, a["lambda0"],
+                        a["zeta"]) for a in v["angular"]]
+    spec = ElementSpec(tm["O"], sfs)
+    G, dG = _acsf_gpu(spec, h2o["positions"], h2o["types"], h2o["box"], None)
+    np.testing.assert_allclose(G[centres], v["expected_values"], rtol=2e-8)
+    np.testing.assert_allclose(dG[0], v["expected_grad_atom0"], atol=6e-9)
+
+
+def test_acsf_ne2_without_box(vec):
+    v = vec["ne2_g2"]
+    spec = ElementSpec(1, [SymFuncSpec(2, v["cutoff"][0], v["cutoff"][1], 1, 0, v["eta"], rs) for rs in v["r_shifts"]])
+    G, _ = _acsf_gpu(spec, np.asarray(v["positions"]), np.ones(2, dtype=np.int32), None)
+    np.testing.assert_allclose(G, np.tile(v["expected_row"], (2, 1)), rtol=1e-8)
+
+
+@pytest.mark.parametrize("cutoff", ["hard", "cos", "tanhu", "tanh", "exp", "poly1", "poly2"])
+def test_acsf_all_cutoffs_vs_oracle(cutoff):
+    pos, types, box = water_box(192, seed=11)
+    rc = 0.9 if cutoff.startswith("poly") else 9.0
+    if cutoff.startswith("poly"):
+        pos, box = pos / 12.0, box / 12.0
+    spec = ElementSpec(2, [
+        SymFuncSpec(1, cutoff, rc, 1), SymFuncSpec(2, cutoff, rc * 0.8, 2, 0, 0.05, 0.5),
+        SymFuncSpec(3, cutoff, rc, 1, 1, 0.01, 0.0, -1.0, 4.0), SymFuncSpec(3, cutoff, rc * 0.9, 1, 2, 0.02, 0.0, 1.0, 2.0),
+        SymFuncSpec(9, cutoff, rc, 2, 2, 0.005, 0.0, 1.0, 1.0), SymFuncSpec(9, cutoff, rc, 2, 1, 0.03, 0.0, -1.0, 3.0),
+        SymFuncSpec(3, cutoff, rc, 2, 2, 0.03, 0.0, 1.0, 2.5)])
+    G_o, dG_o = c_oracle.acsf(spec, pos, types, box)
+    G, dG = _acsf_gpu(spec, pos, types, box)
+    _assert_descriptor_close(G, dG, G_o, dG_o, FP64_TOL)
+
+
+# ------------------------------------------------------------------------------------------ energy / forces
+def _energy_forces_gpu(specs, pos, types, box, dtype=torch.float64):
+    dev = device_potential_from_specs(specs)
+    ws = _workspace(dev, len(pos), dtype)
+    ws.bind(cuda(pos, dtype), cuda(types, torch.int32), box, dev.r_cutoff)
+    e, ea, f = ws.energy_forces(True, True, True)
+    return float(e), ea.cpu().numpy(), f.cpu().numpy()
+
+
+def test_nnp_golden_energy_forces(vec, h2o, pot):
+    e, ea, f = _energy_forces_gpu(pot, h2o["positions"], h2o["types"], h2o["box"])
+    v = vec["nnp_fp32"]
+    np.testing.assert_allclose(e, v["energy"], rtol=0, atol=3e-7)   # float32 golden, see test_oracle_golden.py
+    np.testing.assert_allclose(f, v["forces"], rtol=1e-5, atol=1e-7)
+    eo, eao, fo = c_oracle.energy_forces(pot, h2o["positions"], h2o["types"], h2o["box"])
+    assert rel_err(ea, eao) < FP64_TOL and rel_err(f, fo) < FP64_TOL
+    assert abs(e - eo) < FP64_TOL * np.abs(eao).sum()
+
+
+@pytest.mark.parametrize("n_atoms", [24, 192, 3000])
+def test_energy_forces_water_vs_oracle(n_atoms, pot):
+    pos, types, box = water_box(n_atoms)
+    e, ea, f = _energy_forces_gpu(pot, pos, types, box)
+    eo, eao, fo = c_oracle.energy_forces(pot, pos, types, box)
+    assert rel_err(ea, eao) < FP64_TOL
+    assert rel_err(f, fo) < FP64_TOL
+    assert abs(e - eo) < FP64_TOL * np.abs(eao).sum()
+
+
+@pytest.mark.parametrize("scale_type", ["scale", "scale_center", "scale_center_sigma"])
+def test_energy_forces_scalers(scale_type, pot):
+    pos, types, box = water_box(96, seed=5)
+    specs = [ElementSpec(s.atom_type, s.symfuncs, scale_type, s.scaler, 0.0, 1.0, s.layers) for s in pot]
+    e, ea, f = _energy_forces_gpu(specs, pos, types, box)
+    eo, eao, fo = c_oracle.energy_forces(specs, pos, types, box)
+    assert rel_err(ea, eao) < FP64_TOL and rel_err(f, fo) < FP64_TOL
+
+
+def test_energy_forces_wide_potential_all_activations():
+    pos, types, box = water_box(192, seed=3)
+    specs = rune_width_potential()
+    acts = ["logistic", "softplus", "gaussian", "cos", "exp", "harmonic", "relu", "tanh"]
+    for i, s in enumerate(specs):
+        s.layers = [(k, b, acts[(2 * i + l) % len(acts)] if l < 2 else "identity") for l, (k, b, _) in enumerate(s.layers)]
+    e, ea, f = _energy_forces_gpu(specs, pos, types, box)
+    eo, eao, fo = c_oracle.energy_forces(specs, pos, types, box)
+    assert rel_err(ea, eao) < FP64_TOL and rel_err(f, fo) < FP64_TOL
+
+
+def test_energy_forces_no_box(pot):
+    pos, types, _ = water_box(81, seed=9)
+    e, ea, f = _energy_forces_gpu(pot, pos, types, None)
+    eo, eao, fo = c_oracle.energy_forces(pot, pos, types, None)
+    assert rel_err(ea, eao) < FP64_TOL and rel_err(f, fo) < FP64_TOL
+
+
+def test_energy_forces_fp32_mode(pot):
+    pos, types, box = water_box(192)
+    e, ea, f = _energy_forces_gpu(pot, pos, types, box, torch.float32)
+    eo, eao, fo = c_oracle.energy_forces(pot, pos, types, box)
+    assert rel_err(ea, eao) < FP32_TOL and rel_err(f, fo) < FP32_TOL
+
+
+def test_results_are_bitwise_reproducible(pot):
+    pos, types, box = water_box(3000)
+    a = _energy_forces_gpu(pot, pos, types, box)
+    b = _energy_forces_gpu(pot, pos, types, box)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_owned_range_partition_matches_full(pot):
+    """Multi-GPU ownership: evaluating the atoms in two index blocks gives the same per-atom results."""
+    pos, types, box = water_box(3000)
+    dev = device_potential_from_specs(pot)
+    ws = _workspace(dev, 3000)
+    p, t = cuda(pos), cuda(types, torch.int32)
+    ws.bind(p, t, box, dev.r_cutoff)
+    _, ea_full, f_full = ws.energy_forces(True, True, True)
+    ea, f = torch.zeros_like(ea_full), torch.zeros_like(f_full)
+    for lo, hi in ((0, 1700), (1700, 3000)):
+        ws.bind(p, t, box, dev.r_cutoff, owned=(lo, hi))
+        e_part, ea_part, f_part = ws.energy_forces(True, True, True)
+        ea[lo:hi], f[lo:hi] = ea_part[lo:hi], f_part[lo:hi]
+        assert abs(float(e_part) - float(ea_full[lo:hi].sum())) < 1e-12
+    assert torch.equal(ea, ea_full) and torch.equal(f, f_full)
+
+
+# ------------------------------------------------------------------------------------------ batch (dataset preprocessing)
+def test_batched_structures_match_single(pot):
+    structs = [water_box(192, seed=2024 + s) for s in range(5)]
+    pos = np.concatenate([s[0] for s in structs])
+    types = np.concatenate([s[1] for s in structs])
+    boxes = np.stack([s[2] for s in structs])
+    ptr = np.arange(6, dtype=np.int32) * 192
+    dev = device_potential_from_specs(pot)
+    ws = _workspace(dev, len(pos))
+    ws.bind_batch(cuda(pos), cuda(types, torch.int32), cuda(ptr, torch.int32), cuda(boxes), dev.r_cutoff)
+    for spec in pot:
+        G, dG = ws.acsf(spec.atom_type - 1, len(spec.symfuncs), None, True, True)
+        G, dG = G.cpu().numpy(), dG.cpu().numpy()
+        for s, (p_s, t_s, b_s) in enumerate(structs):
+            G_o, dG_o = c_oracle.acsf(spec, p_s, t_s, b_s)
+            _assert_descriptor_close(G[s * 192:(s + 1) * 192], dG[s * 192:(s + 1) * 192], G_o, dG_o, FP64_TOL)
+
+
+# ------------------------------------------------------------------------------------------ MD
+@pytest.mark.parametrize("n_atoms,n_steps,tau", [(24, 20, 0.0), (192, 10, 25.0), (3000, 4, 0.0)])
+def test_md_run_matches_oracle(n_atoms, n_steps, tau, pot):
+    import ctypes as C
+    from pantea_b200 import _lib
+    pos, types, box = water_box(n_atoms)
+    vel, mass = md_velocities(types), water_masses(types)
+    dt, t0 = 0.25, 300.0
+    p_o, v_o, f_o, sc_o = c_oracle.md_run(pot, pos, vel, mass, types, box, dt, n_steps, t0, tau, KB)
+    dev = device_potential_from_specs(pot)
+    for use_graph in (0, 1):
+        ws = _workspace(dev, n_atoms)
+        p, v, t, m = cuda(pos), cuda(vel), cuda(types, torch.int32), cuda(mass)
+        ws.bind(p, t, box, dev.r_cutoff)
+        _, _, f = ws.energy_forces(False, True)
+        scal = torch.zeros((n_steps, 2), dtype=torch.float64, device="cuda")
+        params = _lib.MDParams(dt, t0, tau, KB, 1, use_graph)
+        _lib.check(_lib.load().pantea_md_run(ws.handle, _lib.ptr(p), _lib.ptr(v), _lib.ptr(f), _lib.ptr(m), _lib.ptr(t),
+                                             n_atoms, _lib.box_arg(box), n_steps, C.byref(params), _lib.ptr(scal),
+                                             _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(p.cpu().numpy(), p_o, rtol=0, atol=1e-10)
+        assert rel_err(v.cpu().numpy(), v_o) < 1e-9
+        assert rel_err(f.cpu().numpy(), f_o) < 1e-8
+        np.testing.assert_allclose(scal.cpu().numpy()[:, 0], sc_o[1:, 0], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(scal.cpu().numpy()[:, 1], sc_o[1:, 1], rtol=1e-9)
