@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Headline benchmark: HDNNP water MD throughput (atom-steps/s) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3                 # this implementation
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 # CPU arm (oracle port on host cores)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3]): 100 000-atom periodic water box, potential tests/golden/h2o.json
+(7 symmetry functions, rc = 12 Bohr, MLPs 3-5-5-1 / 4-5-5-1), NVE velocity Verlet exactly as the
+reference (no mass in the integrator), dt = 0.25 a.u.; strong scaling over the GPUs.
+A "step" is one MD step: position update + wrap, neighbour build, fused symmetry-function / MLP /
+force kernel, velocity update.  One JSON line is printed by rank 0 (contract in the task statement).
+
+Timing: W >= 3 warm-up steps, then K steps each bracketed by CUDA events on the launching stream,
+with an L2 flush (256 MB write) between the timed steps; sum of the K event intervals, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+GOLDEN = ROOT / "tests" / "golden"
+METRIC = "HDNNP MD atom-steps/sec (force evals)"
+UNIT = "atom-steps/s"
+DT = 0.25
+# algorithmic flop weights per unit (SURVEY.md 8d / DESIGN.md): pair, radial-SF (G2), triplet-SF (G3), per-atom rest
+FLOP_PAIR, FLOP_RAD, FLOP_TRIP, FLOP_INTEGRATE = 74.0, 39.0, 160.0, 40.0
+FLOP_MLP = {1: 540.0, 2: 580.0}  # H, O networks of h2o.json (forward + input gradient)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--atoms", type=int, default=int(os.environ.get("PANTEA_BENCH_ATOMS", "100000")))
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostics only: skip the L2 flush between steps")
+    args = ap.parse_args()
+    args.atoms = 3 * (args.atoms // 3)  # whole water molecules: "100 000 atoms" = 33 333 molecules = 99 999 atoms
+    return args
+
+
+def workload_name(n_atoms: int) -> str:
+    return (f"{n_atoms}-atom periodic water box NVE MD, tests/golden/h2o.json HDNNP (rc=12 Bohr), dt=0.25 a.u. "
+            "[BASELINE.json configs[3]]")
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int) -> None:
+        self.proc = None
+        self.index = device_index
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(device_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, power, reasons = [], [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args) -> None:
+    """CPU arm.  The reference's own JAX implementation cannot run here (jax/flax/ase are not installed and there
+    is no network; its dense O(N^3) algorithm could not hold a 100k-atom box anyway), so the oracle port
+    (oracle/hdnnp_oracle.c: same semantics, neighbour lists + analytic gradients, OpenMP) is timed on all host
+    cores on a bounded sample of the same workload: forces for the first M atoms of the same box per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    from oracle.spec import load_potential
+    from pantea_b200.utils.synthetic import water_box
+
+    specs = load_potential(GOLDEN / "h2o.json")
+    pos, types, box = water_box(args.atoms)
+    n = len(pos)
+    threads = c_oracle.num_threads()
+    # size the per-step sample for ~3 s of CPU work
+    t0 = time.perf_counter()
+    c_oracle.energy_forces(specs, pos, types, box, begin=0, end=min(n, 512))
+    rate = min(n, 512) / (time.perf_counter() - t0)
+    m = int(max(256, min(n, rate * 3.0)))
+    for _ in range(args.warmup):
+        c_oracle.energy_forces(specs, pos, types, box, begin=0, end=min(m, 2048))
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        lo = (k * m) % max(n - m, 1)
+        c_oracle.energy_forces(specs, pos, types, box, begin=lo, end=lo + m)
+    elapsed = time.perf_counter() - t0
+    value = m * args.steps / elapsed
+    sample = f"forces+energies of {m} of the {n} atoms per step (cell-list neighbour gather over the full box)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(n), "note": "reference JAX path not runnable here; oracle port timed"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_b200(args) -> None:
+    import torch
+
+    from pantea_b200 import _lib, engine
+    from pantea_b200.distributed import ReplicatedMD, all_reduce_max, init_distributed
+    from pantea_b200.potentials import NeuralNetworkPotential
+    from pantea_b200.utils.synthetic import md_velocities, water_box, water_masses
+    import torch.distributed as dist
+
+    rank, world, local = init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (no CPU fallback on the product path)")
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    code = _lib.dtype_code(dtype)
+
+    nnp = NeuralNetworkPotential.from_runner(GOLDEN / "h2o.json")
+    nnp.load()
+    pot = nnp.device_potential()
+    pos_h, types_h, box_h = water_box(args.atoms)
+    vel_h, mass_h = md_velocities(types_h), water_masses(types_h)
+    n = len(pos_h)
+    box = [float(b) for b in box_h]
+    t = lambda a, dt=dtype: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)  # noqa: E731
+    md = ReplicatedMD(pot, t(pos_h), t(vel_h), t(mass_h), t(types_h, torch.int32), box, DT, rank, world)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush():
+        if not args.no_flush:
+            _lib.check(lib.pantea_l2_flush(_lib.ptr(flush_buf), flush_buf.numel(), _lib.stream_ptr()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then K timed steps ---------------------------------------------------------------
+    warmup = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps
+    for _ in range(warmup):
+        md.step()
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+    launches0 = lib.pantea_launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    flush_launches = 0
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush()
+        flush_launches += 0 if args.no_flush else 1
+        starts[k].record()
+        md.step()
+        stops[k].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = lib.pantea_launch_count() - launches0 - flush_launches
+    ms_total = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+    ms_t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    all_reduce_max(ms_t)
+    ms_total = float(ms_t.item())
+    clocks = sampler.stop() if sampler else None
+    value = n * args.steps / (ms_total * 1e-3)
+
+    # ---- neighbour-capacity check after the run (the timed loop never synchronises) ------------------
+    mx = C.c_int32(0)
+    _lib.check(lib.pantea_neighbor_status(md.ws.handle, C.byref(mx), _lib.stream_ptr()))
+
+    # ---- roofline of the dominant kernel (fused atom kernel), rank 0 ---------------------------------
+    roofline = None
+    extra = {}
+    if rank == 0:
+        counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        _lib.check(lib.pantea_workspace_set_counters(md.ws.handle, _lib.ptr(counters)))
+        md._forces(md.frc_new)
+        torch.cuda.synchronize()
+        _lib.check(lib.pantea_workspace_set_counters(md.ws.handle, None))
+        n_pair, n_rad, n_trip = (int(x) for x in counters[:3].tolist())
+        n_own = md.hi - md.lo
+        own_types = types_h[md.lo:md.hi]
+        flops_kernel = (FLOP_PAIR * n_pair + FLOP_RAD * n_rad + FLOP_TRIP * n_trip
+                        + sum(FLOP_MLP[int(x)] for x in own_types))
+        reps = 5
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in ev:
+            flush()
+            a.record()
+            md._forces(md.frc_new)
+            b.record()
+        torch.cuda.synchronize()
+        k_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+        # measured FMA-pipe peak (the bound of this kernel; MEASURED_PEAKS.json only holds HBM and bf16 tensor peaks)
+        scratch = torch.zeros(16, dtype=torch.float64, device=dev)
+        fl = C.c_double(0.0)
+        peak = 0.0
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(lib.pantea_bench_fma(code, 4096, 148 * 8, 256, _lib.ptr(scratch), C.byref(fl), _lib.stream_ptr()))
+            b.record()
+            torch.cuda.synchronize()
+            peak = max(peak, fl.value / (a.elapsed_time(b) * 1e-3) / 1e12)
+        achieved = flops_kernel / (k_ms * 1e-3) / 1e12
+        traffic = None
+        tfile = ROOT / "profiles" / "traffic.json"
+        if tfile.exists():
+            try:
+                traffic = json.loads(tfile.read_text()).get("hdnnp_atom_kernel_dram_bytes_per_launch")
+            except (ValueError, OSError):
+                traffic = None
+        roofline = {"bound": "fp64_pipe" if dtype == torch.float64 else "fp32_pipe",
+                    "kernel": "hdnnp_atom_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak if peak else None, "traffic": traffic,
+                    "peak_source": "measured live: FMA microbenchmark (pantea_bench_fma), CUDA-core pipe",
+                    "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops_kernel,
+                    "units_per_launch": {"atoms": n_own, "pairs": n_pair, "radial_sf": n_rad, "triplet_sf": n_trip}}
+        extra["kernel_share_of_step"] = k_ms / (ms_total / args.steps)
+        peaks_file = ROOT / "MEASURED_PEAKS.json"
+        if peaks_file.exists():
+            hbm = json.loads(peaks_file.read_text()).get("hbm_gbs")
+            extra["hbm_gbs_measured_peak"] = hbm
+
+    # ---- end-to-end through the public C-ABI path with HOST buffers ---------------------------------
+    # per step: pinned host positions -> device, neighbour build + fused energy/force kernel for the rank's
+    # atoms, forces + energy back to pinned host memory, host waits for the result.
+    e2e_steps = max(3, min(args.steps, 10))
+    host_pos = torch.as_tensor(pos_h, dtype=dtype).pin_memory()
+    host_frc = torch.empty((md.hi - md.lo, 3), dtype=dtype).pin_memory()
+    host_e = torch.empty(1, dtype=dtype).pin_memory()
+    d_pos = torch.empty((n, 3), dtype=dtype, device=dev)
+    d_frc = torch.zeros((n, 3), dtype=dtype, device=dev)
+    d_e = torch.zeros(1, dtype=dtype, device=dev)
+
+    def e2e_step():
+        d_pos.copy_(host_pos, non_blocking=True)
+        md.ws.bind(d_pos, md.types, box, pot.r_cutoff, check=False, owned=(md.lo, md.hi))
+        _lib.check(lib.pantea_energy_forces(md.ws.handle, None, _lib.ptr(d_frc), _lib.ptr(d_e), 0, _lib.stream_ptr()))
+        host_frc.copy_(d_frc[md.lo:md.hi], non_blocking=True)
+        host_e.copy_(d_e, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    all_reduce_max(e2e_t)
+    esz = 8 if dtype == torch.float64 else 4
+    e2e = {"value": n * e2e_steps / float(e2e_t.item()), "unit": UNIT, "h2d_bytes_per_step": n * 3 * esz,
+           "d2h_bytes_per_step": (md.hi - md.lo) * 3 * esz + esz, "steps": e2e_steps,
+           "what": "host positions (pinned) -> pantea_neighbor_build + pantea_energy_forces -> host forces+energy, per rank"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import c_oracle  # the checker, timed as the CPU baseline only
+        from oracle.spec import load_potential
+
+        specs = load_potential(GOLDEN / "h2o.json")
+        t0 = time.perf_counter()
+        c_oracle.energy_forces(specs, pos_h, types_h, box_h, begin=0, end=min(n, 512))
+        rate = min(n, 512) / (time.perf_counter() - t0)
+        m = int(max(256, min(n, rate * 12.0)))
+        t0 = time.perf_counter()
+        c_oracle.energy_forces(specs, pos_h, types_h, box_h, begin=0, end=m)
+        el = time.perf_counter() - t0
+        cpu = {"value": m / el, "unit": UNIT, "cores": c_oracle.num_threads(), "kind": "port",
+               "sample": f"one force+energy evaluation of {m} of the {n} atoms ({el:.1f} s); oracle/hdnnp_oracle.c, "
+                         "OpenMP, cell-list gather; the reference's JAX path cannot run here (no jax)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(n), "atoms": n, "parallelism": f"replicated-coords block-owned x{world}",
+                       "l2": "flushed between timed steps (256 MB write)" if not args.no_flush else "not flushed",
+                       "max_neighbors_seen": int(mx.value), "force_mode": "reference (central-role gradient)"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "wall_s_timed_region": wall,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

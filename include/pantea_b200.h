@@ -192,8 +192,17 @@ int pantea_md_run(pantea_workspace* ws, void* positions, void* velocities, void*
                   const int32_t* types, int64_t n_atoms, const double* box, int64_t n_steps,
                   const pantea_md_params* params, double* scalars, void* stream);
 
-/* counters for bench.py: number of kernel launches issued through this library since load */
+/* -- measurement helpers (bench.py) ------------------------------------------------------------ */
+/* number of kernel launches issued through this library since load */
 int64_t pantea_launch_count(void);
+/* FMA-pipe peak microbenchmark (8 independent chains per thread); *flops = flops of the launch (HOST). */
+int pantea_bench_fma(int32_t dtype, int32_t iters, int32_t blocks, int32_t threads, void* scratch, double* flops,
+                     void* stream);
+/* overwrite `bytes` (> L2 capacity) of DEVICE scratch so that the following kernel sees a cold L2 */
+int pantea_l2_flush(void* scratch, int64_t bytes, void* stream);
+/* optional work counters, DEVICE uint64[4] or NULL: [0] neighbour pairs, [1] radial-SF evaluations,
+   [2] triplet-SF evaluations -- accumulated by every later descriptor / energy launch of `ws` */
+int pantea_workspace_set_counters(pantea_workspace* ws, void* counters);
 
 #ifdef __cplusplus
 }

@@ -154,6 +154,11 @@ def md_run(specs: Sequence[ElementSpec], pos, vel, mass, types, box, dt: float, 
     return pos, vel, forces, scalars
 
 
+def set_use_cells(flag: bool) -> None:
+    """Toggle the cell-list neighbour gather (results are identical either way; tests check that)."""
+    lib().orc_set_use_cells(C.c_int(1 if flag else 0))
+
+
 def num_threads() -> int:
     return int(lib().orc_num_threads())
 

@@ -161,6 +161,68 @@ static int gather_neighbors(const double *p, const double *pos, const int *types
     return cnt;
 }
 
+
+/* ---- optional cell list (same neighbour sets and the same ascending order as the all-pairs scan) ------ */
+typedef struct { int n[3]; double inv[3]; int *head, *next; int active; } orc_cells;
+
+static int orc_cell_coord(double x, double inv, int n) {
+    int c = (int)floor(x * inv);
+    c %= n; if (c < 0) c += n;
+    return c;
+}
+
+static int g_use_cells = 1;
+void orc_set_use_cells(int flag) { g_use_cells = flag; }
+
+static void orc_cells_build(orc_cells *cl, const double *pos, long n, const double *box, double rc) {
+    cl->active = 0; cl->head = cl->next = NULL;
+    if (!box || n < 64 || !g_use_cells) return;
+    double w = rc * (1.0 + 1e-7);
+    for (int k = 0; k < 3; ++k) {
+        cl->n[k] = (int)floor(box[k] / w);
+        if (cl->n[k] < 3) return;
+        if (cl->n[k] > 256) cl->n[k] = 256;
+        cl->inv[k] = cl->n[k] / box[k];
+    }
+    long nc = (long)cl->n[0] * cl->n[1] * cl->n[2];
+    cl->head = (int *)malloc(sizeof(int) * (size_t)nc);
+    cl->next = (int *)malloc(sizeof(int) * (size_t)n);
+    for (long c = 0; c < nc; ++c) cl->head[c] = -1;
+    for (long i = n - 1; i >= 0; --i) { /* reverse insertion -> ascending index inside a cell */
+        int cx = orc_cell_coord(pos[3 * i], cl->inv[0], cl->n[0]), cy = orc_cell_coord(pos[3 * i + 1], cl->inv[1], cl->n[1]),
+            cz = orc_cell_coord(pos[3 * i + 2], cl->inv[2], cl->n[2]);
+        long c = ((long)cz * cl->n[1] + cy) * cl->n[0] + cx;
+        cl->next[i] = cl->head[c]; cl->head[c] = (int)i;
+    }
+    cl->active = 1;
+}
+
+static void orc_cells_free(orc_cells *cl) { free(cl->head); free(cl->next); cl->head = cl->next = NULL; cl->active = 0; }
+
+static int nbr_cmp(const void *a, const void *b) { return ((const orc_nbr *)a)->idx - ((const orc_nbr *)b)->idx; }
+
+static int gather_neighbors_cells(const orc_cells *cl, const double *p, const double *pos, const int *types,
+                                  const double *box, double rc, orc_nbr *out, int cap) {
+    int cnt = 0;
+    int c0[3] = {orc_cell_coord(p[0], cl->inv[0], cl->n[0]), orc_cell_coord(p[1], cl->inv[1], cl->n[1]),
+                 orc_cell_coord(p[2], cl->inv[2], cl->n[2])};
+    for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx_ = -1; dx_ <= 1; ++dx_) {
+        int x = (c0[0] + dx_ + cl->n[0]) % cl->n[0], y = (c0[1] + dy + cl->n[1]) % cl->n[1], z = (c0[2] + dz + cl->n[2]) % cl->n[2];
+        for (int j = cl->head[((long)z * cl->n[1] + y) * cl->n[0] + x]; j >= 0; j = cl->next[j]) {
+            double dx = p[0] - pos[3 * j], dy2 = p[1] - pos[3 * j + 1], dz2 = p[2] - pos[3 * j + 2];
+            dx = min_image(dx, box[0]); dy2 = min_image(dy2, box[1]); dz2 = min_image(dz2, box[2]);
+            double r = norm3(dx, dy2, dz2);
+            if (r <= rc && r > 0.0) {
+                if (cnt < cap) { out[cnt].dx = dx; out[cnt].dy = dy2; out[cnt].dz = dz2; out[cnt].r = r;
+                                 out[cnt].idx = j; out[cnt].type = types[j]; }
+                ++cnt;
+            }
+        }
+    }
+    qsort(out, (size_t)(cnt < cap ? cnt : cap), sizeof(orc_nbr), nbr_cmp);
+    return cnt;
+}
+
 /* Neighbour lists as CSR with ascending columns.  Pass col == NULL to only count.
    Returns total number of neighbours. */
 long orc_neighbors(const double *pos, const int *types, long n, const double *box, double rc, long *row_ptr,
@@ -367,6 +429,8 @@ int orc_energy_forces_range(const orc_element *els, int n_el, const double *pos,
     for (int e = 0; e < n_el; ++e) { double r = max_cutoff(&els[e]); if (r > rc) rc = r; }
     int err = 0;
     double total = 0.0;
+    orc_cells cells;
+    orc_cells_build(&cells, pos, n, box, rc);
 #pragma omp parallel
     {
         orc_nbr *nb = (orc_nbr *)malloc(sizeof(orc_nbr) * (size_t)(n > 0 ? n : 1));
@@ -377,7 +441,8 @@ int orc_energy_forces_range(const orc_element *els, int n_el, const double *pos,
             const orc_element *el = find_element(els, n_el, types[i]);
             double E = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
             if (el && el->n_sf <= ORC_MAX_SF && el->n_layers > 0) {
-                int nn = gather_neighbors(pos + 3 * i, pos, types, n, box, rc, nb, (int)n);
+                int nn = cells.active ? gather_neighbors_cells(&cells, pos + 3 * i, pos, types, box, rc, nb, (int)n)
+                                      : gather_neighbors(pos + 3 * i, pos, types, n, box, rc, nb, (int)n);
                 acsf_one(el, nb, nn, box, G, forces ? dG : NULL, scratch);
                 if (mlp_one(el, G, &E, w) != 0) { err = -1; }
                 if (forces)
@@ -391,6 +456,7 @@ int orc_energy_forces_range(const orc_element *els, int n_el, const double *pos,
         }
         free(nb); free(scratch);
     }
+    orc_cells_free(&cells);
     if (e_sum) *e_sum = total;
     return err;
 }

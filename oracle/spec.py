@@ -167,47 +167,5 @@ def rune_width_potential(seed: int = 7) -> List[ElementSpec]:
 
 
 # ----------------------------------------------------------------------------- synthetic water
-def water_box(n_atoms: int, seed: int = 2024) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Deterministic water box: returns (positions [N,3] wrapped, types [N] (H=1,O=2), box [3])."""
-    assert n_atoms % 3 == 0
-    n_mol = n_atoms // 3
-    rho = 0.0334 / BOHR_PER_ANGSTROM**3  # molecules / Bohr^3
-    L = (n_mol / rho) ** (1.0 / 3.0)
-    m = int(math.ceil(n_mol ** (1.0 / 3.0) - 1e-9))
-    rng = np.random.default_rng(seed)
-    jitter = rng.uniform(-0.15, 0.15, size=(n_mol, 3))
-    quat = rng.standard_normal(size=(n_mol, 4))
-    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
-    idx = np.stack(np.unravel_index(np.arange(n_mol), (m, m, m)), axis=1).astype(np.float64)
-    o = (idx + 0.5 + jitter) * (L / m)
-    w, x, y, z = quat.T
-    rot = np.stack([
-        np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], axis=1),
-        np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], axis=1),
-        np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], axis=1),
-    ], axis=1)  # [n_mol,3,3]
-    half = math.radians(52.26)
-    b = 1.80885
-    h_local = np.array([[math.sin(half), 0.0, math.cos(half)], [-math.sin(half), 0.0, math.cos(half)]]) * b
-    h1 = o + rot @ h_local[0]
-    h2 = o + rot @ h_local[1]
-    pos = np.stack([o, h1, h2], axis=1).reshape(-1, 3)
-    types = np.tile(np.array([2, 1, 1], dtype=np.int32), n_mol)
-    box = np.array([L, L, L])
-    return np.remainder(pos, box), types, box
-
-
-def water_masses(types: np.ndarray) -> np.ndarray:
-    table = {1: MASS_U["H"] * FROM_ATOMIC_MASS, 2: MASS_U["O"] * FROM_ATOMIC_MASS}
-    return np.asarray([table[int(t)] for t in types], dtype=np.float64)
-
-
-def md_velocities(types: np.ndarray, temperature: float = 300.0, seed: int = 2025) -> np.ndarray:
-    """Explicit MD velocities: normal draw, rescale to T, remove COM velocity (pantea/simulation/system.py:91-96)."""
-    n = len(types)
-    m = water_masses(types)[:, None]
-    v = np.random.default_rng(seed).standard_normal((n, 3))
-    t_now = 2 * (0.5 * np.sum(m * v * v)) / (3 * n * KB)
-    v = v * math.sqrt(temperature / t_now)
-    v = v - np.sum(m * v, axis=0) / np.sum(m)
-    return v
+# the generator is shared with bench.py, which may not import oracle/ on the product path
+from pantea_b200.utils.synthetic import md_velocities, water_box, water_masses  # noqa: E402,F401

@@ -73,6 +73,9 @@ PROTOTYPES = {
     "pantea_md_rescale_velocities": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _DBL, _DBL, _DBL, _DBL, _I32, _VP]),
     "pantea_md_run": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I64, C.POINTER(_DBL), _I64, C.POINTER(MDParams), _VP, _VP]),
     "pantea_launch_count": (_I64, []),
+    "pantea_bench_fma": (C.c_int, [_I32, _I32, _I32, _I32, _VP, C.POINTER(_DBL), _VP]),
+    "pantea_l2_flush": (C.c_int, [_VP, _I64, _VP]),
+    "pantea_workspace_set_counters": (C.c_int, [_VP, _VP]),
 }
 
 _lib: Optional[C.CDLL] = None

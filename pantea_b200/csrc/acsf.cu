@@ -6,11 +6,12 @@
 // descriptors/scaler.py:206-246, models/nn/model.py:53-58, potentials/nnp/energy.py:23-66,
 // force.py:16-43).  Work decomposition: WPA warps own one central atom.  The atom's neighbour block
 // (d_ij, r_ij, 1/r_ij, fc, fc' per cutoff class; partitioned by neighbour type) is staged once in
-// shared memory; (j,k) pairs are enumerated flat over the lanes, filtered by the cheap r_jk test and
-// compacted through a per-warp shared-memory queue so that the expensive triplet body always runs
-// with full warps; partial sums are combined with warp shuffles in a fixed order (bitwise
-// reproducible results).  All arithmetic is in T (double or float) on the CUDA cores: the path is
-// FP64/FP32-pipe bound, not a GEMM.
+// shared memory.  For every neighbour j (warp-uniform, its data broadcast from shared memory) the
+// lanes scan the partner neighbours k; pairs surviving the cheap r_jk test are compacted through a
+// per-warp shared-memory queue so that the expensive triplet body (sqrt, two exponentials, one
+// reciprocal, ~100 FP64 instructions) always runs with full warps.  Partial sums are combined with
+// warp shuffles in a fixed order (bitwise reproducible results).  All arithmetic is in T (double or
+// float) on the CUDA cores: the path is FP64/FP32-pipe bound, not a GEMM.
 #include "internal.cuh"
 #include "math.cuh"
 
@@ -18,7 +19,6 @@ namespace pantea {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kAtomsPerBlock = 4;  // WPA == 1 configuration: 4 warps, one atom each
-constexpr int kMCH = 4;            // angular members evaluated per triplet pass
 constexpr int kQueue = 64;         // live-pair queue entries per warp
 
 struct BoxArgK {
@@ -49,6 +49,7 @@ struct AtomArgs {
     int g_stride;
     T* e_atom;
     T* forces;
+    unsigned long long* counters;  // optional work counters: [0] pairs, [1] radial-SF evals, [2] triplet-SF evals
     // shared-memory layout (in units of T unless noted)
     int n_cls_max, n_sf_max, n_neurons_max, width_max;
 };
@@ -77,14 +78,148 @@ __device__ __forceinline__ T powi(T base, int n) {
     return r;
 }
 
+// rarely used, large library routines are kept out of line so that the hot loop stays small
+template <typename T>
+__device__ __noinline__ T pow_general(T base, T e) { return t_pow<T>(base, e); }
+template <typename T>
+__device__ __noinline__ void cutoff_eval_ool(int type, T r, T rc, T* fc, T* dfc) {
+    T a, b;
+    cutoff_eval<T>(type, r, rc, a, b);
+    *fc = a; *dfc = b;
+}
+template <typename T>
+__device__ __noinline__ void activation_eval_ool(int act, T x, T* y, T* dy) {
+    T a, b;
+    activation_eval<T>(act, x, a, b);
+    *y = a; *dy = b;
+}
+
 template <int WPA>
 __device__ __forceinline__ void group_sync() {
     if (WPA == 1) __syncwarp();
     else __syncthreads();
 }
 
-template <typename T, int WPA, bool GRAD>
-__global__ void __launch_bounds__(WPA == 1 ? kAtomsPerBlock * 32 : WPA * 32)
+// per-atom view of the staged neighbour block
+template <typename T>
+struct NbrBlock {
+    const T *dx, *dy, *dz, *r, *inv, *fc, *dfc;  // fc/dfc already offset to the group's cutoff class
+};
+
+// One angular group (same neighbour types, cutoff and kind), MCH members evaluated per triplet.
+template <typename T, int WPA, bool GRAD, int MCH>
+__device__ __forceinline__ void angular_group(const ElementTable& tab, const AngularGroup& grp, int m0, int mc,
+                                              const NbrBlock<T>& nb, int bj, int nj, int bk, int nk, bool wrap_jk, T lx,
+                                              T ly, T lz, int lane, int wrank, T* q_r2, int* q_jk, T* my_acc,
+                                              unsigned long long& cnt_trip) {
+    const bool same = grp.type_j == grp.type_k;
+    const int ctype = tab.cls[grp.cls].type;
+    const T rc = (T)tab.cls[grp.cls].rc;
+    const T inv_rc = (T)1 / rc;
+    const T rc2_incl = rc * rc * ((T)1 + (T)8 * (sizeof(T) == 8 ? (T)2.3e-16 : (T)1.2e-7));
+    const bool is_g3 = grp.kind == PANTEA_G3;
+
+    T m_neta[MCH], m_lam[MCH], m_zl[MCH], m_pref[MCH], m_zm1[MCH];
+    int m_iz[MCH];
+#pragma unroll
+    for (int m = 0; m < MCH; ++m) {
+        const AngularMember mem = tab.members[grp.first + m0 + (m < mc ? m : 0)];
+        m_neta[m] = -(T)mem.eta; m_lam[m] = (T)mem.lambda0; m_pref[m] = (T)mem.pref;
+        m_zl[m] = (T)(mem.pref * mem.zeta * mem.lambda0); m_zm1[m] = (T)(mem.zeta - 1.0);
+        m_iz[m] = mem.izeta;
+    }
+    T aG[MCH], aX[MCH], aY[MCH], aZ[MCH];
+#pragma unroll
+    for (int m = 0; m < MCH; ++m) { aG[m] = 0; aX[m] = 0; aY[m] = 0; aZ[m] = 0; }
+
+    // expensive part for one live (j,k) pair
+    auto triplet = [&](int jk, T rjk2) {
+        const int j = jk & 0xffff, k = jk >> 16;
+        const T dxj = nb.dx[j], dyj = nb.dy[j], dzj = nb.dz[j], rj = nb.r[j], ivj = nb.inv[j], fcj = nb.fc[j];
+        const T dxk = nb.dx[k], dyk = nb.dy[k], dzk = nb.dz[k], rk = nb.r[k], ivk = nb.inv[k], fck = nb.fc[k];
+        T fcjk = (T)1, r2 = rj * rj + rk * rk;
+        if (is_g3) { fcjk = cutoff_value_sq<T>(ctype, rjk2, rc, inv_rc); r2 += rjk2; }
+        const T ivjk = ivj * ivk;
+        const T cost = (dxj * dxk + dyj * dyk + dzj * dzk) * ivjk;
+        const T fjk = fcj * fck;
+        const T fprod = fjk * fcjk;
+        T dfp_j = 0, dfp_k = 0, cj = 0, ck = 0;
+        if (GRAD) {
+            dfp_j = nb.dfc[j] * fck * fcjk; dfp_k = fcj * nb.dfc[k] * fcjk;
+            cj = ivjk - cost * ivj * ivj; ck = ivjk - cost * ivk * ivk;
+        }
+#pragma unroll
+        for (int m = 0; m < MCH; ++m) {
+            if (MCH == 1 || m < mc) {
+                const T e = fast_exp(m_neta[m] * r2);
+                const T bs = (T)1 + m_lam[m] * cost;
+                const T pw1 = m_iz[m] == 1 ? (T)1 : (m_iz[m] > 1 ? powi<T>(bs, m_iz[m] - 1) : pow_general<T>(bs, m_zm1[m]));
+                const T ang_e = m_pref[m] * pw1 * bs * e;
+                aG[m] += ang_e * fprod;
+                if (GRAD) {
+                    const T Tc = m_zl[m] * pw1 * e * fprod;
+                    const T two_neta = (T)2 * m_neta[m];
+                    const T Tij = ang_e * (dfp_j + two_neta * rj * fprod);
+                    const T Tik = ang_e * (dfp_k + two_neta * rk * fprod);
+                    const T Aj = Tc * cj + Tij * ivj, Ak = Tc * ck + Tik * ivk;
+                    aX[m] += Aj * dxj + Ak * dxk;
+                    aY[m] += Aj * dyj + Ak * dyk;
+                    aZ[m] += Aj * dzj + Ak * dzk;
+                }
+            }
+        }
+    };
+
+    int qn = 0;
+    const int kbase = same ? bj : bk;
+    for (int a = wrank; a < nj; a += WPA) {  // neighbour j: uniform within the warp
+        const int j = bj + a;
+        if (nb.fc[j] == (T)0) continue;      // beyond this group's cutoff
+        const T dxj = nb.dx[j], dyj = nb.dy[j], dzj = nb.dz[j];
+        for (int kb = same ? a + 1 : 0; kb < nk; kb += 32) {
+            const int kk = kb + lane;
+            bool live = false;
+            T rjk2 = 0;
+            const int k = kbase + kk;
+            if (kk < nk) {
+                T ex = dxj - nb.dx[k], ey = dyj - nb.dy[k], ez = dzj - nb.dz[k];
+                if (wrap_jk) { ex = min_image(ex, lx); ey = min_image(ey, ly); ez = min_image(ez, lz); }
+                rjk2 = ex * ex + ey * ey + ez * ez;
+                live = rjk2 > (T)0 && (!is_g3 || rjk2 < rc2_incl) && nb.fc[k] != (T)0;
+            }
+            const unsigned mask = __ballot_sync(kFullMask, live);
+            if (live) {
+                const int pos = qn + __popc(mask & ((1u << lane) - 1u));
+                q_jk[pos] = j | (k << 16); q_r2[pos] = rjk2;
+            }
+            qn += __popc(mask);
+            __syncwarp();
+            if (qn >= 32) {
+                qn -= 32;
+                triplet(q_jk[qn + lane], q_r2[qn + lane]);
+                cnt_trip += mc;
+                __syncwarp();
+            }
+        }
+    }
+    if (lane < qn) { triplet(q_jk[lane], q_r2[lane]); cnt_trip += mc; }
+    __syncwarp();
+
+#pragma unroll
+    for (int m = 0; m < MCH; ++m) {
+        if (m < mc) {
+            T g = warp_sum(aG[m]), gx = 0, gy = 0, gz = 0;
+            if (GRAD) { gx = warp_sum(aX[m]); gy = warp_sum(aY[m]); gz = warp_sum(aZ[m]); }
+            if (lane == 0) {
+                T* o = my_acc + 4 * tab.members[grp.first + m0 + m].out;
+                o[0] = g; o[1] = gx; o[2] = gy; o[3] = gz;
+            }
+        }
+    }
+}
+
+template <typename T, int WPA, bool GRAD, int MCH>
+__global__ void __launch_bounds__(WPA == 1 ? kAtomsPerBlock * 32 : WPA * 32, (sizeof(T) == 8 && GRAD) ? 4 : 1)
 hdnnp_atom_kernel(const AtomArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -180,7 +315,7 @@ hdnnp_atom_kernel(const AtomArgs<T> a) {
             sdx[n] = dx; sdy[n] = dy; sdz[n] = dz; sr[n] = r; sinv[n] = (T)1 / r;
             for (int c = 0; c < n_cls; ++c) {
                 T fc, dfc;
-                cutoff_eval<T>(tab.cls[c].type, r, (T)tab.cls[c].rc, fc, dfc);
+                cutoff_eval_ool<T>(tab.cls[c].type, r, (T)tab.cls[c].rc, &fc, &dfc);
                 sfc[c * cap + n] = fc; sdfc[c * cap + n] = dfc;
             }
         }
@@ -188,6 +323,7 @@ hdnnp_atom_kernel(const AtomArgs<T> a) {
     group_sync<WPA>();
 
     T* my_acc = sacc + (size_t)wrank * a.n_sf_max * 4;
+    unsigned long long cnt_rad = 0, cnt_trip = 0;  // per-lane work counters (only summed when requested)
 
     // ---- radial symmetry functions -----------------------------------------------------------------
     for (int s = 0; s < tab.n_radial; ++s) {
@@ -202,10 +338,11 @@ hdnnp_atom_kernel(const AtomArgs<T> a) {
             T val, dval;
             if (sf.kind == PANTEA_G1) { val = fc; dval = dfc; }
             else {
-                const T dr = r - rs, ex = t_exp<T>(-eta * dr * dr);
+                const T dr = r - rs, ex = fast_exp(-eta * dr * dr);
                 val = ex * fc; dval = ex * (dfc - (T)2 * eta * dr * fc);
             }
             g += val;
+            ++cnt_rad;
             if (GRAD) { const T sc = dval * sinv[n]; gx += sc * sdx[n]; gy += sc * sdy[n]; gz += sc * sdz[n]; }
         }
         g = warp_sum(g);
@@ -218,118 +355,19 @@ hdnnp_atom_kernel(const AtomArgs<T> a) {
         const AngularGroup grp = tab.groups[gi];
         const int bj = seg_lo(grp.type_j), nj = seg_hi(grp.type_j) - bj;
         const int bk = seg_lo(grp.type_k), nk = seg_hi(grp.type_k) - bk;
-        const bool same = grp.type_j == grp.type_k;
-        const int P = same ? nj * (nj - 1) / 2 : nj * nk;
-        const int ctype = tab.cls[grp.cls].type;
-        const T rc = (T)tab.cls[grp.cls].rc;
-        const T rc2_incl = rc * rc * ((T)1 + (T)8 * (sizeof(T) == 8 ? (T)2.3e-16 : (T)1.2e-7));
-        const bool is_g3 = grp.kind == PANTEA_G3;
-        const T* fcv = sfc + grp.cls * cap;
-        const T* dfcv = sdfc + grp.cls * cap;
-
-        for (int m0 = 0; m0 < grp.count; m0 += kMCH) {
-            const int mc = grp.count - m0 < kMCH ? grp.count - m0 : kMCH;
-            T m_eta[kMCH], m_lam[kMCH], m_zeta[kMCH], m_pref[kMCH];
-            int m_iz[kMCH];
-#pragma unroll
-            for (int m = 0; m < kMCH; ++m) {
-                const AngularMember mem = tab.members[grp.first + m0 + (m < mc ? m : 0)];
-                m_eta[m] = (T)mem.eta; m_lam[m] = (T)mem.lambda0; m_zeta[m] = (T)mem.zeta; m_pref[m] = (T)mem.pref;
-                m_iz[m] = mem.izeta;
-            }
-            T aG[kMCH], aX[kMCH], aY[kMCH], aZ[kMCH];
-#pragma unroll
-            for (int m = 0; m < kMCH; ++m) { aG[m] = 0; aX[m] = 0; aY[m] = 0; aZ[m] = 0; }
-
-            // expensive part for one live (j,k) pair
-            auto triplet = [&](int jk, T rjk2) {
-                const int j = jk & 0xffff, k = jk >> 16;
-                const T dxj = sdx[j], dyj = sdy[j], dzj = sdz[j], rj = sr[j], ivj = sinv[j], fcj = fcv[j], dfj = dfcv[j];
-                const T dxk = sdx[k], dyk = sdy[k], dzk = sdz[k], rk = sr[k], ivk = sinv[k], fck = fcv[k], dfk = dfcv[k];
-                T fcjk = (T)1, r2 = rj * rj + rk * rk;
-                if (is_g3) { fcjk = cutoff_value<T>(ctype, t_sqrt<T>(rjk2), rc); r2 += rjk2; }
-                const T ivjk = ivj * ivk;
-                const T cost = (dxj * dxk + dyj * dyk + dzj * dzk) * ivjk;
-                const T fprod = fcj * fck * fcjk;
-                const T dfp_j = dfj * fck * fcjk, dfp_k = fcj * dfk * fcjk;
-                const T cj = ivjk - cost * ivj * ivj, ck = ivjk - cost * ivk * ivk;
-#pragma unroll
-                for (int m = 0; m < kMCH; ++m) {
-                    if (m < mc) {
-                        const T e = t_exp<T>(-m_eta[m] * r2);
-                        const T bs = (T)1 + m_lam[m] * cost;
-                        const T pw1 = m_iz[m] >= 1 ? powi<T>(bs, m_iz[m] - 1) : t_pow<T>(bs, m_zeta[m] - (T)1);
-                        const T ang = m_pref[m] * pw1 * bs;
-                        aG[m] += ang * e * fprod;
-                        if (GRAD) {
-                            const T Tc = m_pref[m] * m_zeta[m] * m_lam[m] * pw1 * e * fprod;
-                            const T two_eta = (T)2 * m_eta[m];
-                            const T Tij = ang * e * (dfp_j - two_eta * rj * fprod);
-                            const T Tik = ang * e * (dfp_k - two_eta * rk * fprod);
-                            const T Aj = Tc * cj + Tij * ivj, Ak = Tc * ck + Tik * ivk;
-                            aX[m] += Aj * dxj + Ak * dxk;
-                            aY[m] += Aj * dyj + Ak * dyk;
-                            aZ[m] += Aj * dzj + Ak * dzk;
-                        }
-                    }
-                }
-            };
-
-            // flat enumeration of the pairs: index ia runs fastest (consecutive lanes -> consecutive smem)
-            int p = tid_atom;
-            int ia = 0, ib = 0;
-            if (same) {
-                ib = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-                while (ib * (ib - 1) / 2 > p) --ib;
-                while ((ib + 1) * ib / 2 <= p) ++ib;
-                ia = p - ib * (ib - 1) / 2;
-            } else if (nj > 0) {
-                ib = p / nj; ia = p - ib * nj;
-            }
-            int qn = 0;
-            for (int pbase = 0; pbase < P; pbase += S) {
-                bool live = false;
-                int jk = 0;
-                T rjk2 = 0;
-                if (p < P) {
-                    const int j = bj + ia, k = (same ? bj : bk) + ib;
-                    T ex = sdx[j] - sdx[k], ey = sdy[j] - sdy[k], ez = sdz[j] - sdz[k];
-                    if (wrap_jk) { ex = min_image(ex, lx); ey = min_image(ey, ly); ez = min_image(ez, lz); }
-                    rjk2 = ex * ex + ey * ey + ez * ez;
-                    live = rjk2 > (T)0 && (!is_g3 || rjk2 < rc2_incl) && fcv[j] != (T)0 && fcv[k] != (T)0;
-                    jk = j | (k << 16);
-                    // advance to this thread's next pair
-                    p += S; ia += S;
-                    if (same) { while (ia >= ib) { ia -= ib; ++ib; } }
-                    else { while (ia >= nj) { ia -= nj; ++ib; } }
-                }
-                const unsigned mask = __ballot_sync(kFullMask, live);
-                if (live) {
-                    const int pos = qn + __popc(mask & ((1u << lane) - 1u));
-                    q_jk[pos] = jk; q_r2[pos] = rjk2;
-                }
-                qn += __popc(mask);
-                __syncwarp();
-                if (qn >= 32) {
-                    qn -= 32;
-                    triplet(q_jk[qn + lane], q_r2[qn + lane]);
-                    __syncwarp();
-                }
-            }
-            if (lane < qn) triplet(q_jk[lane], q_r2[lane]);
-            __syncwarp();
-
-#pragma unroll
-            for (int m = 0; m < kMCH; ++m) {
-                if (m < mc) {
-                    T g = warp_sum(aG[m]), gx = 0, gy = 0, gz = 0;
-                    if (GRAD) { gx = warp_sum(aX[m]); gy = warp_sum(aY[m]); gz = warp_sum(aZ[m]); }
-                    if (lane == 0) {
-                        T* o = my_acc + 4 * tab.members[grp.first + m0 + m].out;
-                        o[0] = g; o[1] = gx; o[2] = gy; o[3] = gz;
-                    }
-                }
-            }
+        NbrBlock<T> nb{sdx, sdy, sdz, sr, sinv, sfc + grp.cls * cap, sdfc + grp.cls * cap};
+        for (int m0 = 0; m0 < grp.count; m0 += MCH) {
+            const int mc = grp.count - m0 < MCH ? grp.count - m0 : MCH;
+            angular_group<T, WPA, GRAD, MCH>(tab, grp, m0, mc, nb, bj, nj, bk, nk, wrap_jk, lx, ly, lz, lane, wrank, q_r2,
+                                            q_jk, my_acc, cnt_trip);
+        }
+    }
+    if (a.counters) {
+        cnt_rad = warp_sum(cnt_rad); cnt_trip = warp_sum(cnt_trip);
+        if (lane == 0) {
+            if (wrank == 0) atomicAdd(&a.counters[0], (unsigned long long)total);
+            atomicAdd(&a.counters[1], cnt_rad);
+            atomicAdd(&a.counters[2], cnt_trip);
         }
     }
     group_sync<WPA>();
@@ -377,7 +415,7 @@ hdnnp_atom_kernel(const AtomArgs<T> a) {
             for (int i = 0; i < ni; ++i) z += sh[in_off + i] * (T)W[(size_t)i * no + o];
             z += (T)B[o];
             T y, dy;
-            activation_eval<T>(act, z, y, dy);
+            activation_eval_ool<T>(act, z, &y, &dy);
             sh[out_off + o] = y;
             sdact[out_off - n_sf + o] = dy;
         }
@@ -472,11 +510,11 @@ int reduce_energy(pantea_workspace* ws, const void* e_atom, void* e_total, cudaS
 // ------------------------------------------------------------------------------------------------
 static int g_num_sms = 0;
 
-template <typename T, int WPA, bool GRAD>
+template <typename T, int WPA, bool GRAD, int MCH>
 static int launch_cfg(const AtomArgs<T>& args, size_t per_atom, cudaStream_t st) {
     const int apb = WPA == 1 ? kAtomsPerBlock : 1;
     const size_t smem = per_atom * apb;
-    auto kern = hdnnp_atom_kernel<T, WPA, GRAD>;
+    auto kern = hdnnp_atom_kernel<T, WPA, GRAD, MCH>;
     static size_t configured = 0;  // per instantiation
     if (smem > configured) {
         if (smem > 227 * 1024) return fail(PANTEA_EINVAL, "neighbour capacity / potential too large for shared memory");
@@ -487,6 +525,13 @@ static int launch_cfg(const AtomArgs<T>& args, size_t per_atom, cudaStream_t st)
     kern<<<blocks, apb * WPA * 32, smem, st>>>(args);
     PANTEA_LAUNCH_CHECK();
     return PANTEA_OK;
+}
+
+template <typename T, int WPA, bool GRAD>
+static int launch_mch(const AtomArgs<T>& args, size_t per_atom, int max_members, cudaStream_t st) {
+    if (max_members <= 1) return launch_cfg<T, WPA, GRAD, 1>(args, per_atom, st);
+    if (max_members <= 2) return launch_cfg<T, WPA, GRAD, 2>(args, per_atom, st);
+    return launch_cfg<T, WPA, GRAD, 4>(args, per_atom, st);
 }
 
 template <typename T>
@@ -507,6 +552,7 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
     a.n_work = energy_pass ? (int)ws->n : (int)n_centres;
     a.own_begin = (int)ws->own_begin; a.own_end = ws->own_end < 0 ? (int)ws->n : (int)ws->own_end;
     a.G = (T*)G; a.dG = (T*)dG; a.e_atom = (T*)e_atom; a.forces = (T*)forces;
+    a.counters = ws->counters;
     a.g_stride = element_slot >= 0 ? pot->host[element_slot].n_sf : pot->max_sf;
     a.n_cls_max = pot->max_cls; a.n_sf_max = pot->max_sf > 0 ? pot->max_sf : 1;
     a.n_neurons_max = pot->max_neurons; a.width_max = pot->max_width;
@@ -517,18 +563,20 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
         PANTEA_CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const bool grad = dG != nullptr || forces != nullptr;
+    const int mm = pot->max_members;
     // few atoms: several warps per atom so that every SM sub-partition has work
     const bool wide = (int64_t)a.n_work < (int64_t)g_num_sms * 64;
     if (wide) {
         const size_t per_atom = atom_smem_bytes<T>(a.cap, a.n_cls_max, a.n_sf_max, a.n_neurons_max, a.width_max, 4);
-        return grad ? launch_cfg<T, 4, true>(a, per_atom, st) : launch_cfg<T, 4, false>(a, per_atom, st);
+        return grad ? launch_mch<T, 4, true>(a, per_atom, mm, st) : launch_mch<T, 4, false>(a, per_atom, mm, st);
     }
     const size_t per_atom = atom_smem_bytes<T>(a.cap, a.n_cls_max, a.n_sf_max, a.n_neurons_max, a.width_max, 1);
-    return grad ? launch_cfg<T, 1, true>(a, per_atom, st) : launch_cfg<T, 1, false>(a, per_atom, st);
+    return grad ? launch_mch<T, 1, true>(a, per_atom, mm, st) : launch_mch<T, 1, false>(a, per_atom, mm, st);
 }
 
 int atom_kernel_launch(pantea_workspace* ws, int element_slot, const int32_t* centres, int64_t n_centres, void* G,
                        void* dG, void* e_atom, void* forces, cudaStream_t st) {
+    if (ws->cap > 0xffff) return fail(PANTEA_EINVAL, "max_neighbors must be < 65536");
     if (ws->dtype == PANTEA_F64) return atom_kernel_typed<double>(ws, element_slot, centres, n_centres, G, dG, e_atom, forces, st);
     return atom_kernel_typed<float>(ws, element_slot, centres, n_centres, G, dG, e_atom, forces, st);
 }
@@ -545,7 +593,6 @@ int pantea_acsf_compute(pantea_workspace* ws, int32_t element, const int32_t* ce
     if (ws->mode == kModeNone) return fail(PANTEA_EINVAL, "pantea_acsf_compute: call pantea_neighbor_build first");
     if (element < 0 || element >= ws->pot->n_elements) return fail(PANTEA_EINVAL, "pantea_acsf_compute: element slot out of range");
     if (!G && !dG) return fail(PANTEA_EINVAL, "pantea_acsf_compute: both outputs are NULL");
-    if (ws->cap > 0xffff) return fail(PANTEA_EINVAL, "pantea_acsf_compute: max_neighbors must be < 65536");
     if (!centres) n_centres = ws->n;
     return atom_kernel_launch(ws, element, centres, n_centres, G, dG, nullptr, nullptr, (cudaStream_t)stream);
 }

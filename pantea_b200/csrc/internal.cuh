@@ -91,7 +91,7 @@ struct ElementTable {
 struct pantea_potential {
     int n_elements = 0;
     double rc_max = 0.0;
-    int max_sf = 0, max_cls = 1, max_neurons = 0, max_width = 0;
+    int max_sf = 0, max_cls = 1, max_neurons = 0, max_width = 0, max_members = 1;
     std::vector<pantea::ElementTable> host;
     pantea::ElementTable* dev = nullptr;  // [n_elements]
     std::vector<double*> dev_weights;
@@ -167,7 +167,8 @@ struct pantea_workspace {
     double* e_partial = nullptr;   // reduction scratch
     int64_t e_partial_cap = 0;
     void* md_forces = nullptr;     // [max_atoms,3] F(t+dt) scratch for pantea_md_run
-    double* md_ke = nullptr;       // [1]
+    double* md_ke = nullptr;       // [4]
+    unsigned long long* counters = nullptr;  // optional device work counters [4] (borrowed)
     void* md_eatom = nullptr;      // [max_atoms]
     cudaGraphExec_t md_graph = nullptr;
     cudaStream_t capture_stream = nullptr;

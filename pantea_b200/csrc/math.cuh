@@ -89,6 +89,86 @@ __device__ __forceinline__ void cutoff_eval(int type, T r, T rc, T& fc, T& dfc) 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// branch-free fast paths for the triplet loop (full double accuracy up to ~1 ulp; not IEEE-rounded)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double a) {  // 1/a for normal positive a: MUFU seed + 2 Newton steps
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ float fast_rcp(float a) { return __frcp_rn(a); }
+
+__device__ __forceinline__ double fast_sqrt(double a) {  // sqrt(a) for normal positive a
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a * y, y, 1.0);          // 1 - a y^2
+    y = fma(0.5 * y, e, y);
+    e = fma(-a * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    double s = a * y;
+    return fma(0.5 * y, fma(-s, s, a), s);   // one correction step on the root itself
+}
+__device__ __forceinline__ float fast_sqrt(float a) { return __fsqrt_rn(a); }
+
+// exp(y) for y <= ~700, branch-free: magic-number range reduction, degree-12 polynomial on |f| <= ln2/2,
+// exponent patched in with integer arithmetic; results below ~1e-300 are returned as 0
+__device__ __forceinline__ double fast_exp(double y) {
+    const double shift = 6755399441055744.0;  // 1.5 * 2^52
+    const double yc = fmax(y, -690.0);
+    const double t = fma(yc, 1.4426950408889634, shift);
+    const int k = __double2loint(t);
+    const double kf = t - shift;
+    double f = fma(kf, -6.93147180369123816490e-01, yc);
+    f = fma(kf, -1.90821492927058770002e-10, f);
+    double p = 2.08767569878680989792e-09;              // 1/12!
+    p = fma(p, f, 2.50521083854417187751e-08);          // 1/11!
+    p = fma(p, f, 2.75573192239858906526e-07);          // 1/10!
+    p = fma(p, f, 2.75573192239858906526e-06);          // 1/9!
+    p = fma(p, f, 2.48015873015873015873e-05);          // 1/8!
+    p = fma(p, f, 1.98412698412698412698e-04);          // 1/7!
+    p = fma(p, f, 1.38888888888888888889e-03);          // 1/6!
+    p = fma(p, f, 8.33333333333333333333e-03);          // 1/5!
+    p = fma(p, f, 4.16666666666666666667e-02);          // 1/4!
+    p = fma(p, f, 1.66666666666666666667e-01);          // 1/3!
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    const double r = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    return y < -690.0 ? 0.0 : r;
+}
+__device__ __forceinline__ float fast_exp(float y) { return expf(y); }
+
+__device__ __forceinline__ double cospi_t(double x) { return cospi(x); }
+__device__ __forceinline__ float cospi_t(float x) { return cospif(x); }
+
+// tanh(x) for x in [0, ~20]: 1 - 2/(exp(2x) + 1).  Absolute error ~1e-16 (relative accuracy degrades only where
+// tanh -> 0, i.e. where the cutoff function tanh^3 is itself negligible)
+template <typename T>
+__device__ __forceinline__ T fast_tanh_pos(T x) {
+    return (T)1 - (T)2 * fast_rcp(fast_exp((T)2 * x) + (T)1);
+}
+
+// cutoff value from the squared distance (third leg of G3), hot path
+template <typename T>
+__device__ __forceinline__ T cutoff_value_sq(int type, T r2, T rc, T inv_rc) {
+    const T r = fast_sqrt(r2);
+    if (!(r < rc)) return (T)0;
+    switch (type) {
+        case PANTEA_CUT_TANHU: { const T t = fast_tanh_pos<T>((T)1 - r * inv_rc); return t * t * t; }
+        case PANTEA_CUT_TANH: { const T t = fast_tanh_pos<T>((T)1 - r * inv_rc); return (T)kTanhPre * t * t * t; }
+        case PANTEA_CUT_HARD: return (T)1;
+        case PANTEA_CUT_COS: return (T)0.5 * (cospi_t(r * inv_rc) + (T)1);
+        case PANTEA_CUT_EXP: { const T x = r * inv_rc; return fast_exp((T)1 - fast_rcp((T)1 - x * x)); }
+        case PANTEA_CUT_POLY1: return ((T)2 * r - (T)3) * r * r + (T)1;
+        case PANTEA_CUT_POLY2: return (((T)15 - (T)6 * r) * r - (T)10) * r * r * r + (T)1;
+        default: return (T)0;
+    }
+}
+
 // value only (third leg of G3)
 template <typename T>
 __device__ __forceinline__ T cutoff_value(int type, T r, T rc) {
@@ -123,6 +203,12 @@ __device__ __forceinline__ void activation_eval(int act, T x, T& y, T& dy) {
         case PANTEA_ACT_HARMONIC: y = x * x; dy = (T)2 * x; break;
         default: y = x; dy = (T)1; break;
     }
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 
 template <typename T>

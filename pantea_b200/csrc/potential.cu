@@ -155,6 +155,7 @@ int pantea_potential_create(const pantea_potential_desc* desc, pantea_potential*
         if (t.rc_max > pot->rc_max) pot->rc_max = t.rc_max;
         if (t.n_sf > pot->max_sf) pot->max_sf = t.n_sf;
         if (t.n_cls > pot->max_cls) pot->max_cls = t.n_cls;
+        for (int g = 0; g < t.n_groups; ++g) if (t.groups[g].count > pot->max_members) pot->max_members = t.groups[g].count;
         if (t.n_neurons > pot->max_neurons) pot->max_neurons = t.n_neurons;
         for (int l = 0; l <= t.n_layers; ++l)
             if (t.n_layers > 0 && t.sizes[l] > pot->max_width) pot->max_width = t.sizes[l];

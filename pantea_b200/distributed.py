@@ -1,0 +1,162 @@
+"""Multi-GPU molecular dynamics: one process per GPU over torch.distributed (NCCL on NVLink/NVSwitch).
+
+Round-1 scheme -- *replicated coordinates, partitioned work*: every rank keeps all N positions
+(24 B/atom; 24 MB at 1 M atoms) but owns a contiguous block of atoms.  Per step a rank integrates
+its block, the blocks are exchanged with ONE in-place `all_gather_into_tensor` (the only data-path
+collective; forces in the reference's central-role definition need no reverse communication,
+SURVEY fact 3), every rank bins all atoms into the global cell grid, and builds neighbour rows +
+evaluates the fused energy/force kernel for its own block only.  Scalars (E, KE) are all-reduced on
+demand.  SURVEY section 8(e) names this all-gather as the legitimate first implementation and as
+the cross-check for a halo-exchange version.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed() -> Tuple[int, int, int]:
+    """(rank, world, local_rank) from the torchrun environment; initialises the process group if needed."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return rank, world, local
+
+
+@dataclass
+class BlockLayout:
+    """Contiguous, equally sized ownership blocks (the last one may be short)."""
+
+    n_atoms: int
+    rank: int
+    world: int
+
+    @property
+    def block(self) -> int:
+        return (self.n_atoms + self.world - 1) // self.world
+
+    @property
+    def padded(self) -> int:
+        return self.block * self.world
+
+    def owned(self, rank: Optional[int] = None) -> Tuple[int, int]:
+        r = self.rank if rank is None else rank
+        lo = min(r * self.block, self.n_atoms)
+        return lo, min(lo + self.block, self.n_atoms)
+
+    def allocate(self, like: torch.Tensor) -> torch.Tensor:
+        """Padded [padded, 3] buffer whose first n rows are the atoms; rank r's block is rows [r*block, (r+1)*block)."""
+        buf = torch.zeros((self.padded, 3), dtype=like.dtype, device=like.device)
+        buf[: self.n_atoms] = like
+        return buf
+
+    def exchange(self, buf: torch.Tensor) -> None:
+        """In-place all-gather: each rank contributes its own block of `buf`."""
+        if self.world == 1:
+            return
+        flat = buf.view(-1)
+        mine = flat[self.rank * self.block * 3:(self.rank + 1) * self.block * 3]
+        dist.all_gather_into_tensor(flat, mine)
+
+
+def all_reduce_sum(t: torch.Tensor) -> torch.Tensor:
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def all_reduce_max(t: torch.Tensor) -> torch.Tensor:
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t
+
+
+class ReplicatedMD:
+    """Velocity-Verlet MD of one periodic box on `world` GPUs (reference integrator, no mass)."""
+
+    def __init__(self, device_potential, positions: torch.Tensor, velocities: torch.Tensor, masses: torch.Tensor,
+                 types: torch.Tensor, box: Sequence[float], time_step: float, rank: int = 0, world: int = 1,
+                 thermostat=None, kb: float = 3.166811563e-6) -> None:
+        from pantea_b200 import _lib, engine
+
+        self._lib, self.lib = _lib, _lib.load()
+        self.pot = device_potential
+        n = int(positions.shape[0])
+        self.layout = BlockLayout(n, rank, world)
+        self.n, self.dt, self.box = n, float(time_step), list(box)
+        self.dtype, self.code = positions.dtype, _lib.dtype_code(positions.dtype)
+        self.pos_buf = self.layout.allocate(positions)
+        self.pos = self.pos_buf[:n]
+        self.vel = velocities.clone().contiguous()
+        self.mass = masses.reshape(-1).to(self.dtype).contiguous()
+        self.types = types.to(torch.int32).contiguous()
+        self.frc = torch.zeros((n, 3), dtype=self.dtype, device=positions.device)
+        self.frc_new = torch.zeros_like(self.frc)
+        self.e_atom = torch.zeros(n, dtype=self.dtype, device=positions.device)
+        self.thermostat, self.kb = thermostat, kb
+        self.ke = torch.zeros(1, dtype=torch.float64, device=positions.device)
+        density = n / (self.box[0] * self.box[1] * self.box[2])
+        self.ws = engine.Workspace(device_potential, n, engine.estimate_max_neighbors(device_potential.r_cutoff, density, n),
+                                   self.dtype)
+        self.lo, self.hi = self.layout.owned()
+        self.steps = 0
+        self._bind(check=True)
+        self._forces(self.frc)
+
+    def _bind(self, check: bool = False) -> None:
+        self.ws.bind(self.pos, self.types, self.box, self.pot.r_cutoff, check=check, owned=(self.lo, self.hi))
+
+    def _forces(self, out: torch.Tensor, e_atom: Optional[torch.Tensor] = None) -> None:
+        _lib = self._lib
+        _lib.check(self.lib.pantea_energy_forces(self.ws.handle, _lib.ptr(e_atom), _lib.ptr(out), None, 0, _lib.stream_ptr()))
+
+    def step(self) -> None:
+        _lib, lib = self._lib, self.lib
+        st = _lib.stream_ptr()
+        box_c = _lib.box_arg(self.box)
+        _lib.check(lib.pantea_md_update_positions(_lib.ptr(self.pos_buf), _lib.ptr(self.vel), _lib.ptr(self.frc),
+                                                  self.lo, self.hi, box_c, self.dt, self.code, st))
+        self.layout.exchange(self.pos_buf)
+        self._bind()
+        self._forces(self.frc_new)
+        _lib.check(lib.pantea_md_update_velocities(_lib.ptr(self.vel), _lib.ptr(self.frc), _lib.ptr(self.frc_new),
+                                                   self.lo, self.hi, self.dt, self.code, st))
+        if self.thermostat is not None:
+            self.kinetic_energy()
+            _lib.check(lib.pantea_md_rescale_velocities(_lib.ptr(self.vel), self.lo, self.hi, _lib.ptr(self.ke), self.n,
+                                                        self.dt, self.thermostat.time_constant,
+                                                        self.thermostat.target_temperature, self.kb, self.code, st))
+        self.steps += 1
+
+    def kinetic_energy(self) -> torch.Tensor:
+        _lib = self._lib
+        _lib.check(self.lib.pantea_md_kinetic_energy(_lib.ptr(self.vel), _lib.ptr(self.mass), self.lo, self.hi,
+                                                     _lib.ptr(self.ke), self.code, _lib.stream_ptr()))
+        return all_reduce_sum(self.ke)
+
+    def potential_energy(self) -> torch.Tensor:
+        self._forces(self.frc_new, self.e_atom)  # frc_new is scratch between steps
+        e = self.e_atom[self.lo:self.hi].double().sum().reshape(1)
+        return all_reduce_sum(e)
+
+    def gather_owned(self, t: torch.Tensor) -> torch.Tensor:
+        """Assemble a full [n, 3] array from every rank's owned rows (diagnostics / tests)."""
+        if self.layout.world == 1:
+            return t
+        buf = self.layout.allocate(t)
+        self.layout.exchange(buf)
+        return buf[: self.n]

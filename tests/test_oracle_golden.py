@@ -195,3 +195,14 @@ def test_md_c_oracle_matches_dense_steps(pot):
     np.testing.assert_allclose(p1, x.numpy(), rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(v1, v.numpy(), rtol=1e-10, atol=1e-14)
     assert sc.shape == (4, 3) and np.isfinite(sc).all()
+
+
+def test_c_oracle_cell_list_is_bitwise_identical_to_all_pairs(pot):
+    pos, types, box = water_box(3000)
+    c_oracle.set_use_cells(False)
+    try:
+        e0, ea0, f0 = c_oracle.energy_forces(pot, pos, types, box)
+    finally:
+        c_oracle.set_use_cells(True)
+    e1, ea1, f1 = c_oracle.energy_forces(pot, pos, types, box)
+    assert np.array_equal(ea0, ea1) and np.array_equal(f0, f1)
