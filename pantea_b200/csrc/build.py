@@ -39,6 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     objdir = HERE / "build"
     objdir.mkdir(exist_ok=True)
     common = [nvcc, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", f"-I{ROOT / 'include'}", f"-I{HERE}"]
+    common += os.environ.get("PANTEA_DEFINES", "").split()
     if verbose:
         common += ["-Xptxas", "-v"]
     procs = []

@@ -137,6 +137,7 @@ struct pantea_workspace {
     const pantea_potential* pot = nullptr;
     int64_t max_atoms = 0;
     int cap = 0;    // neighbours per row
+    int smem_cap = 0;  // rows staged in shared memory by the atom kernel (0: cap); set from the observed maximum
     int dtype = PANTEA_F64;
     int n_types = 0;  // buckets used by the potential (others -> bucket n_types)
 

@@ -365,7 +365,6 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
             ca = CellArg{nc[0], nc[1], nc[2], nc[0] / box[0], nc[1] / box[1], nc[2] / box[2]};
         }
     }
-    PANTEA_CUDA_TRY(cudaMemsetAsync(ws->flags, 0, 16, st));
     if (use_cells) {
         const int64_t ncells = (int64_t)ca.nx * ca.ny * ca.nz;
         int rcode = ensure_cell_capacity(ws, ncells);
@@ -438,8 +437,19 @@ int pantea_neighbor_status(pantea_workspace* ws, int32_t* max_count, void* strea
     if (!ws) return fail(PANTEA_EINVAL, "pantea_neighbor_status: NULL workspace");
     int32_t h[4] = {0, 0, 0, 0};
     PANTEA_CUDA_TRY(cudaMemcpyAsync(h, ws->flags, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PANTEA_CUDA_TRY(cudaMemsetAsync(ws->flags, 0, 16, (cudaStream_t)stream));  // maxima are sticky until read
     PANTEA_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     if (max_count) *max_count = h[0];
+    if (h[1] > 0)
+        return fail(PANTEA_ECAPACITY, "neighbour block overflow in the atom kernel: " + std::to_string(h[1]) +
+                                          " neighbours > staged capacity " + std::to_string(ws->smem_cap));
+    if (h[0] <= ws->cap) {
+        // shared-memory footprint of the atom kernel follows the observed maximum (+10 % + 8 head-room)
+        int want = (h[0] + h[0] / 10 + 8 + 7) / 8 * 8;
+        if (want < 32) want = 32;
+        if (want > ws->cap) want = ws->cap;
+        if (want > ws->smem_cap || want < ws->smem_cap - 32) ws->smem_cap = want;
+    }
     if (h[0] > ws->cap)
         return fail(PANTEA_ECAPACITY, "neighbour row overflow: " + std::to_string(h[0]) + " neighbours > capacity " +
                                           std::to_string(ws->cap));

@@ -98,7 +98,7 @@ class DescriptorScaler:
     def partial_fit(cls, params: ScalerParams, data: Array) -> ScalerParams:
         data = torch.atleast_2d(data)
         new = cls.fit(data)
-        m, n = params.nsamples, data.shape[0]
+        m, n = params.nsamples.to(data.dtype), data.shape[0]  # fractions in the data precision, not torch's float32 default
         fm, fn = m / (m + n), n / (m + n)
         diff = params.mean - new.mean
         mean = fm * params.mean + fn * new.mean

@@ -1,0 +1,51 @@
+"""The C-ABI shared library loads and exports exactly the symbols declared in include/pantea_b200.h.
+No compute call is made (there is no GPU in the CPU test run)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "pantea_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pantea_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    from pantea_b200 import _lib
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in pantea_b200.h but not exported"
+    assert sorted(_lib.PROTOTYPES) == declared      # the Python binding covers the whole header, nothing else
+
+
+def test_error_convention_without_gpu():
+    import torch
+    from pantea_b200 import _lib
+    lib = _lib.load()
+    assert lib.pantea_version().startswith(b"pantea_b200")
+    assert lib.pantea_launch_count() >= 0
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    assert lib.pantea_device_count() == 0
+    handle = ctypes.c_void_p()
+    code = lib.pantea_workspace_create(None, 64, 32, 64, ctypes.byref(handle))
+    assert code == _lib.PANTEA_ECUDA and b"no CUDA device" in lib.pantea_last_error()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.require_cuda()
+    assert lib.pantea_workspace_create(None, 64, 32, 16, ctypes.byref(handle)) == _lib.PANTEA_EINVAL
+    with pytest.raises(ValueError):
+        _lib.check(lib.pantea_workspace_set_owned_range(None, 0, 1))
+
+
+def test_product_package_never_imports_the_oracle():
+    offenders = [p for p in (ROOT / "pantea_b200").rglob("*.py") if re.search(r"^\s*(from|import)\s+oracle\b", p.read_text(), re.M)]
+    assert offenders == []
