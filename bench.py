@@ -109,6 +109,20 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # the real thing first: the unmodified reference installed (--no-deps) under baseline/_ref
+    ref_status = "baseline/_ref not present"
+    ref_dir = ROOT / "baseline" / "_ref"
+    if ref_dir.exists():
+        sys.path.insert(0, str(ref_dir))
+        try:
+            from pantea.potentials import NeuralNetworkPotential as _RefNNP  # noqa: F401
+            ref_status = "importable"
+        except Exception as exc:  # ModuleNotFoundError: jax (not installable: no network, no wheel)
+            ref_status = f"pantea.potentials not importable: {type(exc).__name__}: {exc}"
+        finally:
+            sys.path.remove(str(ref_dir))
+            for mod in [m for m in sys.modules if m == "pantea" or m.startswith("pantea.")]:
+                del sys.modules[mod]
     from oracle import c_oracle
     from oracle.spec import load_potential
     from pantea_b200.utils.synthetic import water_box
@@ -135,7 +149,8 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(n), "note": "reference JAX path not runnable here; oracle port timed"},
+        "config": {"workload": workload_name(n), "note": "reference JAX path not runnable here; oracle port timed",
+                   "reference_install": ref_status},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

@@ -26,12 +26,15 @@ def init_distributed() -> Tuple[int, int, int]:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        import datetime
+
         backend = "nccl" if torch.cuda.is_available() else "gloo"
+        timeout = datetime.timedelta(seconds=int(os.environ.get("PANTEA_DIST_TIMEOUT_S", "600")))
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+            dist.init_process_group(backend, device_id=torch.device("cuda", local), timeout=timeout)
         else:
-            dist.init_process_group(backend)
+            dist.init_process_group(backend, timeout=timeout)
     elif torch.cuda.is_available():
         torch.cuda.set_device(local)
     return rank, world, local
@@ -146,12 +149,12 @@ class ReplicatedMD:
         _lib = self._lib
         _lib.check(self.lib.pantea_md_kinetic_energy(_lib.ptr(self.vel), _lib.ptr(self.mass), self.lo, self.hi,
                                                      _lib.ptr(self.ke), self.code, _lib.stream_ptr()))
-        return all_reduce_sum(self.ke)
+        return all_reduce_sum(self.ke) if self.layout.world > 1 else self.ke
 
     def potential_energy(self) -> torch.Tensor:
         self._forces(self.frc_new, self.e_atom)  # frc_new is scratch between steps
         e = self.e_atom[self.lo:self.hi].double().sum().reshape(1)
-        return all_reduce_sum(e)
+        return all_reduce_sum(e) if self.layout.world > 1 else e
 
     def gather_owned(self, t: torch.Tensor) -> torch.Tensor:
         """Assemble a full [n, 3] array from every rank's owned rows (diagnostics / tests)."""
