@@ -1,25 +1,39 @@
-// Fused per-atom HDNNP kernel for sm_100a:
-//   neighbour block staging -> radial (G1/G2) and angular (G3/G9) symmetry functions with analytic
-//   central-role gradients -> scaler -> per-element MLP forward/backward -> energy and force.
+// HDNNP symmetry-function / network / force kernels for sm_100a.
 //
 // Replaces the reference's vmap/scan/autodiff pipeline (pantea/descriptors/acsf/acsf.py:163-330,
 // descriptors/scaler.py:206-246, models/nn/model.py:53-58, potentials/nnp/energy.py:23-66,
-// force.py:16-43).  Work decomposition: WPA warps own one central atom.  The atom's neighbour block
-// (d_ij, r_ij, 1/r_ij, fc, fc' per cutoff class; partitioned by neighbour type) is staged once in
-// shared memory.  For every neighbour j (warp-uniform, its data broadcast from shared memory) the
-// lanes scan the partner neighbours k; pairs surviving the cheap r_jk test are compacted through a
-// per-warp shared-memory queue so that the expensive triplet body (sqrt, two exponentials, one
-// reciprocal, ~100 FP64 instructions) always runs with full warps.  Partial sums are combined with
-// warp shuffles in a fixed order (bitwise reproducible results).  All arithmetic is in T (double or
-// float) on the CUDA cores: the path is FP64/FP32-pipe bound, not a GEMM.
+// force.py:16-43) with two launches per evaluation:
+//
+//  1. `pair_filter_kernel` (FP32 / integer pipes, high occupancy).  One warp per central atom stages a float4
+//     copy of its neighbour vectors in shared memory and, for every angular group (type_j, type_k, cutoff, kind),
+//     scans the (j,k) neighbour pairs -- j warp-uniform, lanes over k, 64 partners per iteration -- keeping those
+//     whose r_jk^2 lies below a slightly inclusive single-precision bound.  Survivors are ballot-compacted into a
+//     per-atom pair list in global memory (coalesced 4-byte stores, deterministic order).
+//  2. `hdnnp_eval_kernel` (FP64 / FP32 arithmetic pipe).  WPA warps per central atom stage the full-precision
+//     neighbour block (d_ij, r_ij, 1/r_ij, fc, fc' per cutoff class; structure-of-arrays) in shared memory,
+//     evaluate the radial functions (lanes over neighbours) and walk the pair lists flat: every lane evaluates NU
+//     independent triplets per iteration (r_jk recomputed exactly; the reference's r_jk > 0 and r_jk < rc tests are
+//     applied here), so the ~100-FP64-instruction triplet body runs with full warps and NU independent dependency
+//     chains.  Warp-shuffle reductions in a fixed order (bitwise reproducible), then scaler -> MLP forward /
+//     backward (lanes over neurons) -> E_i and F_i = -sum_s dE_i/dG_s dG_s/dr_i (central-role gradient: no scatter).
+//
+// All arithmetic is on the CUDA cores: the path is FP64/FP32-pipe bound, not a GEMM.
 #include "internal.cuh"
 #include "math.cuh"
+
+#ifndef PANTEA_EVAL_MINBLOCKS
+#define PANTEA_EVAL_MINBLOCKS 4  // resident 128-thread blocks per SM the FP64 evaluation kernel is compiled for
+#endif
+#ifndef PANTEA_TRIPLETS_PER_LANE
+#define PANTEA_TRIPLETS_PER_LANE 1
+#endif
 
 namespace pantea {
 
 constexpr unsigned kFullMask = 0xffffffffu;
-constexpr int kAtomsPerBlock = 4;  // WPA == 1 configuration: 4 warps, one atom each
-constexpr int kQueue = 64;         // live-pair queue entries per warp
+constexpr int kAtomsPerBlock = 4;   // eval kernel, WPA == 1 configuration: 4 warps, one atom each
+constexpr int kFilterWarps = 8;     // pair filter: 8 warps per block, one atom each
+constexpr int kNU = PANTEA_TRIPLETS_PER_LANE;
 
 struct BoxArgK {
     double lx, ly, lz;
@@ -31,12 +45,15 @@ struct AtomArgs {
     const Rec<T>* rec;
     const int32_t* nbr;
     const int32_t* tcount;
-    int cap;
+    int cap;   // row stride of `nbr`
+    int scap;  // neighbour records staged in shared memory (<= cap; longer rows raise the overflow flag)
+    int32_t* flags;
     const int32_t* slot_of;
     const int32_t* struct_of;
     const double* boxes;
     BoxArgK box;
     int wrap_jk;
+    double rc_list;  // radius the neighbour rows were built with
     const ElementTable* tables;
     int n_types;
     int element_slot;  // >= 0: apply this element's table to every centre; -1: the atom's own type
@@ -44,27 +61,27 @@ struct AtomArgs {
     int n_work;
     int by_slot;  // 1: work item = cell-sorted slot (energy/force pass); 0: work item = centre list entry
     int own_begin, own_end;
+    // pair lists written by the filter, read by the evaluation
+    int32_t* pairs;      // [n_work][pair_cap]  (j | k << 16), row positions within the staged neighbour block
+    int32_t* pair_off;   // [n_work][max_groups + 1] offsets of each group's segment
+    int pair_cap, max_groups;
     T* G;
     T* dG;
     int g_stride;
     T* e_atom;
     T* forces;
     unsigned long long* counters;  // optional work counters: [0] pairs, [1] radial-SF evals, [2] triplet-SF evals
-    // shared-memory layout (in units of T unless noted)
     int n_cls_max, n_sf_max, n_neurons_max, width_max;
 };
 
 template <typename T>
-__host__ __device__ inline size_t atom_smem_bytes(int cap, int n_cls, int n_sf, int n_neurons, int width, int wpa) {
-    size_t t_elems = (size_t)(5 + 2 * n_cls) * cap   // neighbour block
+__host__ __device__ inline size_t eval_smem_bytes(int cap, int n_cls, int n_sf, int n_neurons, int width, int wpa) {
+    size_t t_elems = (size_t)(5 + 2 * n_cls) * cap   // neighbour block (structure of arrays)
                      + (size_t)wpa * n_sf * 4        // per-warp partial sums
                      + (size_t)(n_sf + n_neurons)    // layer activations
                      + (size_t)n_neurons             // activation derivatives
                      + 2 * (size_t)(width > n_sf ? width : n_sf);  // back-propagation ping-pong
-    size_t bytes = t_elems * sizeof(T);
-    bytes = (bytes + 7) & ~size_t(7);
-    bytes += (size_t)wpa * kQueue * (sizeof(T) + sizeof(int));  // live-pair queues
-    return (bytes + 15) & ~size_t(15);
+    return (t_elems * sizeof(T) + 15) & ~size_t(15);
 }
 
 template <typename T>
@@ -78,7 +95,7 @@ __device__ __forceinline__ T powi(T base, int n) {
     return r;
 }
 
-// rarely used, large library routines are kept out of line so that the hot loop stays small
+// rarely used, large library routines are kept out of line so that the hot loops stay small
 template <typename T>
 __device__ __noinline__ T pow_general(T base, T e) { return t_pow<T>(base, e); }
 template <typename T>
@@ -100,31 +117,181 @@ __device__ __forceinline__ void group_sync() {
     else __syncthreads();
 }
 
-// per-atom view of the staged neighbour block
+// work item -> (cell-ordered slot, output row, element table); false when the item is not evaluated
 template <typename T>
-struct NbrBlock {
-    const T *dx, *dy, *dz, *r, *inv, *fc, *dfc;  // fc/dfc already offset to the group's cutoff class
+__device__ __forceinline__ bool resolve_item(const AtomArgs<T>& a, int w, int& slot, int& out_row, int& etype) {
+    if (a.by_slot) {
+        slot = w;
+        out_row = rec_idx(a.rec[slot]);
+        if (out_row < a.own_begin || out_row >= a.own_end) return false;
+    } else {
+        const int oi = a.centres ? a.centres[w] : w;
+        slot = a.slot_of[oi];
+        out_row = w;
+    }
+    etype = a.element_slot >= 0 ? a.element_slot : rec_type(a.rec[slot]);
+    return true;
+}
+
+template <typename T>
+__device__ __forceinline__ void item_box(const AtomArgs<T>& a, int slot, T& lx, T& ly, T& lz, bool& pbc) {
+    lx = (T)a.box.lx; ly = (T)a.box.ly; lz = (T)a.box.lz;
+    pbc = a.box.has_box != 0;
+    if (a.boxes) {
+        const int s = a.struct_of[slot];
+        lx = (T)a.boxes[3 * s]; ly = (T)a.boxes[3 * s + 1]; lz = (T)a.boxes[3 * s + 2];
+        pbc = true;
+    }
+}
+
+// neighbour segments by type bucket: seg[b] .. seg[b+1] within the (type-partitioned) row, clamped to `total`
+struct Segments {
+    int seg[kBuckets + 1];
+    int total;
+    __device__ __forceinline__ void load(const int32_t* tc, int cap) {
+        int acc = 0;
+#pragma unroll
+        for (int b = 0; b < kBuckets; ++b) { seg[b] = acc; acc += tc[b]; }
+        seg[kBuckets] = acc;
+        total = acc < cap ? acc : cap;
+    }
+    __device__ __forceinline__ int lo(int t) const {
+        int v = 0;
+#pragma unroll
+        for (int b = 0; b < kBuckets; ++b) if (b == t) v = seg[b];
+        return v < total ? v : total;
+    }
+    __device__ __forceinline__ int hi(int t) const {
+        int v = 0;
+#pragma unroll
+        for (int b = 0; b < kBuckets; ++b) if (b == t) v = seg[b + 1];
+        return v < total ? v : total;
+    }
 };
 
-// One angular group (same neighbour types, cutoff and kind), MCH members evaluated per triplet.
-template <typename T, int WPA, bool GRAD, int MCH>
+// ------------------------------------------------------------------------------------------------
+// 1. pair pre-filter
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const AtomArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * kFilterWarps + wib;
+    if (w >= a.n_work) return;
+    int slot, out_row, etype;
+    if (!resolve_item(a, w, slot, out_row, etype)) return;
+    int32_t* off_out = a.pair_off + (size_t)w * (a.max_groups + 1);
+    if (etype >= a.n_types) {
+        if (lane == 0) off_out[0] = 0;
+        return;
+    }
+    const ElementTable& tab = a.tables[etype];
+    float4* sf4 = (float4*)smem_raw + (size_t)wib * a.scap;
+
+    Segments sg;
+    sg.load(a.tcount + (size_t)slot * kBuckets, a.scap);
+    if (sg.seg[kBuckets] > a.scap && lane == 0) atomicMax(&a.flags[1], sg.seg[kBuckets]);
+
+    T lx, ly, lz;
+    bool pbc;
+    item_box(a, slot, lx, ly, lz, pbc);
+    const bool wrap_jk = pbc && a.wrap_jk;
+    const float flx = (float)lx, fly = (float)ly, flz = (float)lz;
+
+    // stage (dx, dy, dz, cutoff-class bit mask): differences formed in T, then rounded to float
+    {
+        const Rec<T> ri = a.rec[slot];
+        const int32_t* row = a.nbr + (size_t)slot * a.cap;
+        const int n_cls = tab.n_cls;
+        for (int n = lane; n < sg.total; n += 32) {
+            const Rec<T> rj = a.rec[row[n]];
+            T dx = sub_rn(ri.x, rj.x), dy = sub_rn(ri.y, rj.y), dz = sub_rn(ri.z, rj.z);
+            if (pbc) { dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz); }
+            const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
+            const float r2 = fx * fx + fy * fy + fz * fz;
+            int bits = 0;
+            for (int c = 0; c < n_cls; ++c) {
+                const float rcf = (float)tab.cls[c].rc;
+                bits |= (r2 < rcf * rcf * 1.0001f + 1e-4f) ? (1 << c) : 0;  // inclusive: exact test in the evaluation
+            }
+            sf4[n] = make_float4(fx, fy, fz, __int_as_float(bits));
+        }
+    }
+    __syncwarp();
+
+    int32_t* list = a.pairs + (size_t)w * a.pair_cap;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int off = 0;  // running number of pairs (may exceed pair_cap: then only counted)
+    for (int gi = 0; gi < tab.n_groups; ++gi) {
+        if (lane == 0) off_out[gi] = off < a.pair_cap ? off : a.pair_cap;
+        const AngularGroup grp = tab.groups[gi];
+        const int bj = sg.lo(grp.type_j), nj = sg.hi(grp.type_j) - bj;
+        const int bk = sg.lo(grp.type_k), nk = sg.hi(grp.type_k) - bk;
+        const bool same = grp.type_j == grp.type_k;
+        const float rcf = (float)tab.cls[grp.cls].rc;
+        const float rc2f = grp.kind == PANTEA_G3 ? rcf * rcf * 1.0001f + 1e-4f : 3.0e38f;
+        const int cls_bit = 1 << grp.cls;
+        const int kbase = same ? bj : bk;
+        for (int aj = 0; aj < nj; ++aj) {  // neighbour j: uniform within the warp
+            const int j = bj + aj;
+            const float4 fj = sf4[j];
+            if (!(__float_as_int(fj.w) & cls_bit)) continue;  // beyond this group's cutoff
+            for (int kb = same ? aj + 1 : 0; kb < nk; kb += 64) {  // two 32-wide chunks of partners k per iteration
+                bool live[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int kk = kb + 32 * c + lane;
+                    const float4 fk = sf4[kbase + (kk < nk ? kk : 0)];
+                    float ex = fj.x - fk.x, ey = fj.y - fk.y, ez = fj.z - fk.z;
+                    if (wrap_jk) { ex = min_image(ex, flx); ey = min_image(ey, fly); ez = min_image(ez, flz); }
+                    const float d2 = ex * ex + ey * ey + ez * ez;
+                    live[c] = kk < nk && d2 < rc2f && (__float_as_int(fk.w) & cls_bit);
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const unsigned mask = __ballot_sync(kFullMask, live[c]);
+                    const int pos = off + __popc(mask & lt_mask);
+                    if (live[c] && pos < a.pair_cap) list[pos] = j | ((kbase + kb + 32 * c + lane) << 16);
+                    off += __popc(mask);
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        off_out[tab.n_groups] = off < a.pair_cap ? off : a.pair_cap;
+        atomicMax(&a.flags[2], off);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. evaluation
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct NbrBlock {
+    const T *dx, *dy, *dz, *r, *inv, *fc, *dfc;  // fc / dfc already offset to the group's cutoff class
+};
+
+// One angular group (same neighbour types, cutoff and kind), members [m0, m0 + mc), flat over the pair list.
+// FAST: compile-time specialisation for the common RuNNer setting -- G3, tanhu cutoff, zeta == 1 for every member
+// -- whose triplet body is straight-line code; otherwise kind / cutoff / zeta are runtime (warp-uniform) branches.
+template <typename T, int WPA, bool GRAD, int MCH, bool FAST>
 __device__ __forceinline__ void angular_group(const ElementTable& tab, const AngularGroup& grp, int m0, int mc,
-                                              const NbrBlock<T>& nb, int bj, int nj, int bk, int nk, bool wrap_jk, T lx,
-                                              T ly, T lz, int lane, int wrank, T* q_r2, int* q_jk, T* my_acc,
+                                              const NbrBlock<T>& nb, const int32_t* __restrict__ list, int count,
+                                              bool wrap_jk, T lx, T ly, T lz, int lane, int tid_atom, T* my_acc,
                                               unsigned long long& cnt_trip) {
-    const bool same = grp.type_j == grp.type_k;
+    constexpr int NU = kNU;
+    constexpr int S = 32 * WPA;
     const int ctype = tab.cls[grp.cls].type;
     const T rc = (T)tab.cls[grp.cls].rc;
     const T inv_rc = (T)1 / rc;
-    const T rc2_incl = rc * rc * ((T)1 + (T)8 * (sizeof(T) == 8 ? (T)2.3e-16 : (T)1.2e-7));
-    const bool is_g3 = grp.kind == PANTEA_G3;
+    const bool is_g3 = FAST ? true : grp.kind == PANTEA_G3;
 
-    T m_neta[MCH], m_lam[MCH], m_zl[MCH], m_pref[MCH], m_zm1[MCH];
+    T m_neta[MCH], m_2neta[MCH], m_lam[MCH], m_zl[MCH], m_pref[MCH], m_zm1[MCH];
     int m_iz[MCH];
 #pragma unroll
     for (int m = 0; m < MCH; ++m) {
         const AngularMember mem = tab.members[grp.first + m0 + (m < mc ? m : 0)];
-        m_neta[m] = -(T)mem.eta; m_lam[m] = (T)mem.lambda0; m_pref[m] = (T)mem.pref;
+        m_neta[m] = -(T)mem.eta; m_2neta[m] = (T)(-2.0 * mem.eta); m_lam[m] = (T)mem.lambda0; m_pref[m] = (T)mem.pref;
         m_zl[m] = (T)(mem.pref * mem.zeta * mem.lambda0); m_zm1[m] = (T)(mem.zeta - 1.0);
         m_iz[m] = mem.izeta;
     }
@@ -132,78 +299,93 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
 #pragma unroll
     for (int m = 0; m < MCH; ++m) { aG[m] = 0; aX[m] = 0; aY[m] = 0; aZ[m] = 0; }
 
-    // expensive part for one live (j,k) pair
-    auto triplet = [&](int jk, T rjk2) {
-        const int j = jk & 0xffff, k = jk >> 16;
-        const T dxj = nb.dx[j], dyj = nb.dy[j], dzj = nb.dz[j], rj = nb.r[j], ivj = nb.inv[j], fcj = nb.fc[j];
-        const T dxk = nb.dx[k], dyk = nb.dy[k], dzk = nb.dz[k], rk = nb.r[k], ivk = nb.inv[k], fck = nb.fc[k];
-        T fcjk = (T)1, r2 = rj * rj + rk * rk;
-        if (is_g3) { fcjk = cutoff_value_sq<T>(ctype, rjk2, rc, inv_rc); r2 += rjk2; }
-        const T ivjk = ivj * ivk;
-        const T cost = (dxj * dxk + dyj * dyk + dzj * dzk) * ivjk;
-        const T fjk = fcj * fck;
-        const T fprod = fjk * fcjk;
-        T dfp_j = 0, dfp_k = 0, cj = 0, ck = 0;
-        if (GRAD) {
-            dfp_j = nb.dfc[j] * fck * fcjk; dfp_k = fcj * nb.dfc[k] * fcjk;
-            cj = ivjk - cost * ivj * ivj; ck = ivjk - cost * ivk * ivk;
+    for (int base = 0; base < count; base += S * NU) {
+        int jk[NU];
+        bool valid[NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int e = base + u * S + tid_atom;
+            valid[u] = e < count;
+            jk[u] = list[valid[u] ? e : 0];
+        }
+        T dxj[NU], dyj[NU], dzj[NU], rj[NU], ivj[NU], fcj[NU], dxk[NU], dyk[NU], dzk[NU], rk[NU], ivk[NU], fck[NU];
+        T dfj[NU], dfk[NU], r2[NU], rjk2[NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int j = jk[u] & 0xffff, k = jk[u] >> 16;
+            dxj[u] = nb.dx[j]; dyj[u] = nb.dy[j]; dzj[u] = nb.dz[j]; rj[u] = nb.r[j]; ivj[u] = nb.inv[j]; fcj[u] = nb.fc[j];
+            dxk[u] = nb.dx[k]; dyk[u] = nb.dy[k]; dzk[u] = nb.dz[k]; rk[u] = nb.r[k]; ivk[u] = nb.inv[k]; fck[u] = nb.fc[k];
+            dfj[u] = GRAD ? nb.dfc[j] : (T)0; dfk[u] = GRAD ? nb.dfc[k] : (T)0;
+        }
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {  // r_jk = |pbc(d_ij - d_ik)| (reference acsf.py:316-320), exact
+            T ex = dxj[u] - dxk[u], ey = dyj[u] - dyk[u], ez = dzj[u] - dzk[u];
+            if (wrap_jk) { ex = min_image(ex, lx); ey = min_image(ey, ly); ez = min_image(ez, lz); }
+            rjk2[u] = ex * ex + ey * ey + ez * ez;
+            valid[u] = valid[u] && rjk2[u] > (T)0;  // k == j / coincident atoms excluded (acsf.py:325)
+            r2[u] = rj[u] * rj[u] + rk[u] * rk[u];
+        }
+        T fcjk[NU];
+        if (FAST) {
+            T rjk[NU], t[NU];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) rjk[u] = fast_sqrt(valid[u] ? rjk2[u] : (T)1);
+#pragma unroll
+            for (int u = 0; u < NU; ++u) t[u] = fast_tanh_pos<T>((T)1 - rjk[u] * inv_rc);
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                fcjk[u] = (valid[u] && rjk[u] < rc) ? t[u] * t[u] * t[u] : (T)0;
+                r2[u] += rjk2[u];
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                fcjk[u] = (T)1;
+                if (is_g3) { fcjk[u] = cutoff_value_sq<T>(ctype, valid[u] ? rjk2[u] : (T)1, rc, inv_rc); r2[u] += rjk2[u]; }
+                if (!valid[u]) fcjk[u] = (T)0;
+            }
+        }
+        T ivjk[NU], cost[NU], fprod[NU], dfp_j[NU], dfp_k[NU], cj[NU], ck[NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            ivjk[u] = ivj[u] * ivk[u];
+            cost[u] = (dxj[u] * dxk[u] + dyj[u] * dyk[u] + dzj[u] * dzk[u]) * ivjk[u];
+            fprod[u] = fcj[u] * fck[u] * fcjk[u];
+            if (GRAD) {
+                dfp_j[u] = dfj[u] * fck[u] * fcjk[u]; dfp_k[u] = fcj[u] * dfk[u] * fcjk[u];
+                cj[u] = ivjk[u] - cost[u] * ivj[u] * ivj[u]; ck[u] = ivjk[u] - cost[u] * ivk[u] * ivk[u];
+            }
         }
 #pragma unroll
         for (int m = 0; m < MCH; ++m) {
             if (MCH == 1 || m < mc) {
-                const T e = fast_exp(m_neta[m] * r2);
-                const T bs = (T)1 + m_lam[m] * cost;
-                const T pw1 = m_iz[m] == 1 ? (T)1 : (m_iz[m] > 1 ? powi<T>(bs, m_iz[m] - 1) : pow_general<T>(bs, m_zm1[m]));
-                const T ang_e = m_pref[m] * pw1 * bs * e;
-                aG[m] += ang_e * fprod;
-                if (GRAD) {
-                    const T Tc = m_zl[m] * pw1 * e * fprod;
-                    const T two_neta = (T)2 * m_neta[m];
-                    const T Tij = ang_e * (dfp_j + two_neta * rj * fprod);
-                    const T Tik = ang_e * (dfp_k + two_neta * rk * fprod);
-                    const T Aj = Tc * cj + Tij * ivj, Ak = Tc * ck + Tik * ivk;
-                    aX[m] += Aj * dxj + Ak * dxk;
-                    aY[m] += Aj * dyj + Ak * dyk;
-                    aZ[m] += Aj * dzj + Ak * dzk;
+                T e[NU];
+#pragma unroll
+                for (int u = 0; u < NU; ++u) e[u] = fast_exp(m_neta[m] * r2[u]);
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    const T bs = (T)1 + m_lam[m] * cost[u];
+                    T pw1 = (T)1;
+                    if (!FAST && m_iz[m] != 1) pw1 = m_iz[m] > 1 ? powi<T>(bs, m_iz[m] - 1) : pow_general<T>(bs, m_zm1[m]);
+                    const T ang_e = m_pref[m] * pw1 * bs * e[u];
+                    aG[m] += ang_e * fprod[u];
+                    if (GRAD) {
+                        const T Tc = m_zl[m] * pw1 * e[u] * fprod[u];
+                        const T Tij = ang_e * (dfp_j[u] + m_2neta[m] * rj[u] * fprod[u]);
+                        const T Tik = ang_e * (dfp_k[u] + m_2neta[m] * rk[u] * fprod[u]);
+                        const T Aj = Tc * cj[u] + Tij * ivj[u], Ak = Tc * ck[u] + Tik * ivk[u];
+                        aX[m] += Aj * dxj[u] + Ak * dxk[u];
+                        aY[m] += Aj * dyj[u] + Ak * dyk[u];
+                        aZ[m] += Aj * dzj[u] + Ak * dzk[u];
+                    }
                 }
             }
         }
-    };
-
-    int qn = 0;
-    const int kbase = same ? bj : bk;
-    for (int a = wrank; a < nj; a += WPA) {  // neighbour j: uniform within the warp
-        const int j = bj + a;
-        if (nb.fc[j] == (T)0) continue;      // beyond this group's cutoff
-        const T dxj = nb.dx[j], dyj = nb.dy[j], dzj = nb.dz[j];
-        for (int kb = same ? a + 1 : 0; kb < nk; kb += 32) {
-            const int kk = kb + lane;
-            bool live = false;
-            T rjk2 = 0;
-            const int k = kbase + kk;
-            if (kk < nk) {
-                T ex = dxj - nb.dx[k], ey = dyj - nb.dy[k], ez = dzj - nb.dz[k];
-                if (wrap_jk) { ex = min_image(ex, lx); ey = min_image(ey, ly); ez = min_image(ez, lz); }
-                rjk2 = ex * ex + ey * ey + ez * ez;
-                live = rjk2 > (T)0 && (!is_g3 || rjk2 < rc2_incl) && nb.fc[k] != (T)0;
-            }
-            const unsigned mask = __ballot_sync(kFullMask, live);
-            if (live) {
-                const int pos = qn + __popc(mask & ((1u << lane) - 1u));
-                q_jk[pos] = j | (k << 16); q_r2[pos] = rjk2;
-            }
-            qn += __popc(mask);
-            __syncwarp();
-            if (qn >= 32) {
-                qn -= 32;
-                triplet(q_jk[qn + lane], q_r2[qn + lane]);
-                cnt_trip += mc;
-                __syncwarp();
-            }
+        if (cnt_trip != ~0ull) {
+#pragma unroll
+            for (int u = 0; u < NU; ++u) cnt_trip += (valid[u] && fcjk[u] != (T)0) ? (unsigned long long)mc : 0ull;
         }
     }
-    if (lane < qn) { triplet(q_jk[lane], q_r2[lane]); cnt_trip += mc; }
-    __syncwarp();
 
 #pragma unroll
     for (int m = 0; m < MCH; ++m) {
@@ -219,8 +401,8 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
 }
 
 template <typename T, int WPA, bool GRAD, int MCH>
-__global__ void __launch_bounds__(WPA == 1 ? kAtomsPerBlock * 32 : WPA * 32, (sizeof(T) == 8 && GRAD) ? 4 : 1)
-hdnnp_atom_kernel(const AtomArgs<T> a) {
+__global__ void __launch_bounds__(WPA == 1 ? kAtomsPerBlock * 32 : WPA * 32, (sizeof(T) == 8 && GRAD) ? PANTEA_EVAL_MINBLOCKS : 1)
+hdnnp_eval_kernel(const AtomArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int atom_in_block = WPA == 1 ? wib : 0;
@@ -230,20 +412,8 @@ hdnnp_atom_kernel(const AtomArgs<T> a) {
     const int w = blockIdx.x * (WPA == 1 ? kAtomsPerBlock : 1) + atom_in_block;
     if (w >= a.n_work) return;
 
-    // ---- resolve the central atom ---------------------------------------------------------------
-    int slot, out_row;
-    if (a.by_slot) {
-        slot = w;
-        const int oi0 = rec_idx(a.rec[slot]);
-        if (oi0 < a.own_begin || oi0 >= a.own_end) return;
-        out_row = oi0;
-    } else {
-        const int oi0 = a.centres ? a.centres[w] : w;
-        slot = a.slot_of[oi0];
-        out_row = w;
-    }
-    const Rec<T> ri = a.rec[slot];
-    const int etype = a.element_slot >= 0 ? a.element_slot : rec_type(ri);
+    int slot, out_row, etype;
+    if (!resolve_item(a, w, slot, out_row, etype)) return;
     if (etype >= a.n_types) {  // an atom no element network describes: contributes nothing
         if (tid_atom == 0) {
             if (a.e_atom) a.e_atom[out_row] = (T)0;
@@ -253,82 +423,77 @@ hdnnp_atom_kernel(const AtomArgs<T> a) {
     }
     const ElementTable& tab = a.tables[etype];
     const int n_sf = tab.n_sf;
+    const Rec<T> ri = a.rec[slot];
 
-    T lx = (T)a.box.lx, ly = (T)a.box.ly, lz = (T)a.box.lz;
-    bool pbc = a.box.has_box != 0;
-    if (a.boxes) {
-        const int s = a.struct_of[slot];
-        lx = (T)a.boxes[3 * s]; ly = (T)a.boxes[3 * s + 1]; lz = (T)a.boxes[3 * s + 2];
-        pbc = true;
-    }
+    T lx, ly, lz;
+    bool pbc;
+    item_box(a, slot, lx, ly, lz, pbc);
     const bool wrap_jk = pbc && a.wrap_jk;
 
     // ---- carve shared memory ---------------------------------------------------------------------
-    const int cap = a.cap;
-    const size_t per_atom = atom_smem_bytes<T>(cap, a.n_cls_max, a.n_sf_max, a.n_neurons_max, a.width_max, WPA);
-    unsigned char* base = smem_raw + (size_t)atom_in_block * per_atom;
-    T* sdx = (T*)base;
+    const int cap = a.scap;
+    const size_t per_atom = eval_smem_bytes<T>(cap, a.n_cls_max, a.n_sf_max, a.n_neurons_max, a.width_max, WPA);
+    T* sdx = (T*)(smem_raw + (size_t)atom_in_block * per_atom);
     T* sdy = sdx + cap;
     T* sdz = sdy + cap;
     T* sr = sdz + cap;
     T* sinv = sr + cap;
-    T* sfc = sinv + cap;                       // [n_cls_max][cap]
-    T* sdfc = sfc + (size_t)a.n_cls_max * cap; // [n_cls_max][cap]
-    T* sacc = sdfc + (size_t)a.n_cls_max * cap;  // [WPA][n_sf_max][4]
-    T* sh = sacc + (size_t)WPA * a.n_sf_max * 4; // [n_sf_max + n_neurons_max]
+    T* sfc = sinv + cap;                          // [n_cls_max][cap]
+    T* sdfc = sfc + (size_t)a.n_cls_max * cap;    // [n_cls_max][cap]
+    T* sacc = sdfc + (size_t)a.n_cls_max * cap;   // [WPA][n_sf_max][4]
+    T* sh = sacc + (size_t)WPA * a.n_sf_max * 4;  // [n_sf_max + n_neurons_max]
     T* sdact = sh + a.n_sf_max + a.n_neurons_max;
     const int gw = a.width_max > a.n_sf_max ? a.width_max : a.n_sf_max;
     T* sg0 = sdact + a.n_neurons_max;
     T* sg1 = sg0 + gw;
-    size_t t_bytes = ((size_t)((sg1 + gw) - sdx) * sizeof(T) + 7) & ~size_t(7);
-    T* q_r2 = (T*)(base + t_bytes) + (size_t)wrank * kQueue;
-    int* q_jk = (int*)(base + t_bytes + (size_t)WPA * kQueue * sizeof(T)) + (size_t)wrank * kQueue;
 
-    // ---- neighbour segments by type ----------------------------------------------------------------
-    int seg[kBuckets + 1];
-    {
-        const int32_t* tc = a.tcount + (size_t)slot * kBuckets;
-        int acc = 0;
-#pragma unroll
-        for (int b = 0; b < kBuckets; ++b) { seg[b] = acc; acc += tc[b]; }
-        seg[kBuckets] = acc;
-    }
-    const int total = seg[kBuckets] < cap ? seg[kBuckets] : cap;
-    auto seg_lo = [&](int t) { int v = 0;
-#pragma unroll
-        for (int b = 0; b < kBuckets; ++b) if (b == t) v = seg[b];
-        return v < total ? v : total; };
-    auto seg_hi = [&](int t) { int v = 0;
-#pragma unroll
-        for (int b = 0; b < kBuckets; ++b) if (b == t) v = seg[b + 1];
-        return v < total ? v : total; };
+    Segments sg;
+    sg.load(a.tcount + (size_t)slot * kBuckets, cap);
+    const int total = sg.total;
 
-    // ---- stage the neighbour block -----------------------------------------------------------------
+    // ---- stage the neighbour block (two neighbours per thread in flight: gather latency) ------------
     {
-        const int32_t* row = a.nbr + (size_t)slot * cap;
+        const int32_t* row = a.nbr + (size_t)slot * a.cap;
         const int n_cls = tab.n_cls;
-        for (int n = tid_atom; n < total; n += S) {
-            const Rec<T> rj = a.rec[row[n]];
-            T dx = sub_rn(ri.x, rj.x), dy = sub_rn(ri.y, rj.y), dz = sub_rn(ri.z, rj.z);
-            if (pbc) { dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz); }
-            const T r = norm3_rn(dx, dy, dz);
-            sdx[n] = dx; sdy[n] = dy; sdz[n] = dz; sr[n] = r; sinv[n] = (T)1 / r;
-            for (int c = 0; c < n_cls; ++c) {
-                T fc, dfc;
-                cutoff_eval_ool<T>(tab.cls[c].type, r, (T)tab.cls[c].rc, &fc, &dfc);
-                sfc[c * cap + n] = fc; sdfc[c * cap + n] = dfc;
+        for (int n0 = tid_atom; n0 < total; n0 += 2 * S) {
+            const int n1 = n0 + S;
+            const bool has1 = n1 < total;
+            const int i0 = row[n0], i1 = row[has1 ? n1 : n0];
+            const Rec<T> ra = a.rec[i0], rb = a.rec[i1];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !has1) break;
+                const Rec<T>& rj = u == 0 ? ra : rb;
+                const int n = u == 0 ? n0 : n1;
+                T dx = sub_rn(ri.x, rj.x), dy = sub_rn(ri.y, rj.y), dz = sub_rn(ri.z, rj.z);
+                if (pbc) { dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz); }
+                const T r = norm3_rn(dx, dy, dz);
+                sdx[n] = dx; sdy[n] = dy; sdz[n] = dz; sr[n] = r; sinv[n] = (T)1 / r;
+                for (int c = 0; c < n_cls; ++c) {
+                    T fc, dfc;
+                    const int ct = tab.cls[c].type;
+                    const T rcc = (T)tab.cls[c].rc;
+                    if (ct == PANTEA_CUT_TANHU) {  // inline fast path for the common cutoff
+                        const T t = fast_tanh_pos<T>((T)1 - r / rcc), t2 = t * t;
+                        const bool in = r < rcc;
+                        fc = in ? t2 * t : (T)0; dfc = in ? ((T)-3 / rcc) * t2 * ((T)1 - t2) : (T)0;
+                    } else {
+                        cutoff_eval_ool<T>(ct, r, rcc, &fc, &dfc);
+                    }
+                    sfc[c * cap + n] = fc; sdfc[c * cap + n] = dfc;
+                }
             }
         }
     }
     group_sync<WPA>();
 
     T* my_acc = sacc + (size_t)wrank * a.n_sf_max * 4;
-    unsigned long long cnt_rad = 0, cnt_trip = 0;  // per-lane work counters (only summed when requested)
+    unsigned long long cnt_rad = 0, cnt_trip = a.counters ? 0ull : ~0ull;  // work counters (~0: disabled)
 
     // ---- radial symmetry functions -----------------------------------------------------------------
     for (int s = 0; s < tab.n_radial; ++s) {
         const RadialSF sf = tab.radial[s];
-        const int lo = seg_lo(sf.type_j), hi = seg_hi(sf.type_j);
+        const int lo = sg.lo(sf.type_j), hi = sg.hi(sf.type_j);
         const T eta = (T)sf.eta, rs = (T)sf.r_shift;
         const T* fcv = sfc + sf.cls * cap;
         const T* dfcv = sdfc + sf.cls * cap;
@@ -350,16 +515,25 @@ hdnnp_atom_kernel(const AtomArgs<T> a) {
         if (lane == 0) { T* o = my_acc + 4 * sf.out; o[0] = g; o[1] = gx; o[2] = gy; o[3] = gz; }
     }
 
-    // ---- angular symmetry functions ------------------------------------------------------------------
-    for (int gi = 0; gi < tab.n_groups; ++gi) {
-        const AngularGroup grp = tab.groups[gi];
-        const int bj = seg_lo(grp.type_j), nj = seg_hi(grp.type_j) - bj;
-        const int bk = seg_lo(grp.type_k), nk = seg_hi(grp.type_k) - bk;
-        NbrBlock<T> nb{sdx, sdy, sdz, sr, sinv, sfc + grp.cls * cap, sdfc + grp.cls * cap};
-        for (int m0 = 0; m0 < grp.count; m0 += MCH) {
-            const int mc = grp.count - m0 < MCH ? grp.count - m0 : MCH;
-            angular_group<T, WPA, GRAD, MCH>(tab, grp, m0, mc, nb, bj, nj, bk, nk, wrap_jk, lx, ly, lz, lane, wrank, q_r2,
-                                            q_jk, my_acc, cnt_trip);
+    // ---- angular symmetry functions: flat walk over the pre-filtered pair lists ---------------------
+    {
+        const int32_t* offs = a.pair_off + (size_t)w * (a.max_groups + 1);
+        const int32_t* lists = a.pairs + (size_t)w * a.pair_cap;
+        for (int gi = 0; gi < tab.n_groups; ++gi) {
+            const AngularGroup grp = tab.groups[gi];
+            const int lo = offs[gi], count = offs[gi + 1] - lo;
+            NbrBlock<T> nb{sdx, sdy, sdz, sr, sinv, sfc + grp.cls * cap, sdfc + grp.cls * cap};
+            bool fast = tab.cls[grp.cls].type == PANTEA_CUT_TANHU && grp.kind == PANTEA_G3;
+            for (int m = 0; m < grp.count; ++m) fast = fast && tab.members[grp.first + m].izeta == 1;
+            for (int m0 = 0; m0 < grp.count; m0 += MCH) {
+                const int mc = grp.count - m0 < MCH ? grp.count - m0 : MCH;
+                if (fast)
+                    angular_group<T, WPA, GRAD, MCH, true>(tab, grp, m0, mc, nb, lists + lo, count, wrap_jk, lx, ly, lz, lane,
+                                                           tid_atom, my_acc, cnt_trip);
+                else
+                    angular_group<T, WPA, GRAD, MCH, false>(tab, grp, m0, mc, nb, lists + lo, count, wrap_jk, lx, ly, lz, lane,
+                                                            tid_atom, my_acc, cnt_trip);
+            }
         }
     }
     if (a.counters) {
@@ -511,10 +685,10 @@ int reduce_energy(pantea_workspace* ws, const void* e_atom, void* e_total, cudaS
 static int g_num_sms = 0;
 
 template <typename T, int WPA, bool GRAD, int MCH>
-static int launch_cfg(const AtomArgs<T>& args, size_t per_atom, cudaStream_t st) {
+static int launch_eval(const AtomArgs<T>& args, cudaStream_t st) {
     const int apb = WPA == 1 ? kAtomsPerBlock : 1;
-    const size_t smem = per_atom * apb;
-    auto kern = hdnnp_atom_kernel<T, WPA, GRAD, MCH>;
+    const size_t smem = apb * eval_smem_bytes<T>(args.scap, args.n_cls_max, args.n_sf_max, args.n_neurons_max, args.width_max, WPA);
+    auto kern = hdnnp_eval_kernel<T, WPA, GRAD, MCH>;
     static size_t configured = 0;  // per instantiation
     if (smem > configured) {
         if (smem > 227 * 1024) return fail(PANTEA_EINVAL, "neighbour capacity / potential too large for shared memory");
@@ -528,50 +702,91 @@ static int launch_cfg(const AtomArgs<T>& args, size_t per_atom, cudaStream_t st)
 }
 
 template <typename T, int WPA, bool GRAD>
-static int launch_mch(const AtomArgs<T>& args, size_t per_atom, int max_members, cudaStream_t st) {
-    if (max_members <= 1) return launch_cfg<T, WPA, GRAD, 1>(args, per_atom, st);
-    if (max_members <= 2) return launch_cfg<T, WPA, GRAD, 2>(args, per_atom, st);
-    return launch_cfg<T, WPA, GRAD, 4>(args, per_atom, st);
+static int launch_mch(const AtomArgs<T>& a, int max_members, cudaStream_t st) {
+    if (max_members <= 1) return launch_eval<T, WPA, GRAD, 1>(a, st);
+    return launch_eval<T, WPA, GRAD, 4>(a, st);
+}
+
+template <typename T>
+static int launch_filter(const AtomArgs<T>& a, cudaStream_t st) {
+    const size_t smem = (size_t)kFilterWarps * a.scap * sizeof(float4);
+    auto kern = pair_filter_kernel<T>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (smem > 227 * 1024) return fail(PANTEA_EINVAL, "neighbour capacity too large for shared memory");
+        PANTEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int blocks = (a.n_work + kFilterWarps - 1) / kFilterWarps;
+    kern<<<blocks, kFilterWarps * 32, smem, st>>>(a);
+    PANTEA_LAUNCH_CHECK();
+    return PANTEA_OK;
+}
+
+// pair-list storage: [max_atoms][pair_cap] entries + [max_atoms][max_groups + 1] offsets
+static int ensure_pair_storage(pantea_workspace* ws) {
+    const pantea_potential* pot = ws->pot;
+    const int scap = ws->smem_cap > 0 && ws->smem_cap < ws->cap ? ws->smem_cap : ws->cap;
+    int want = ws->pair_cap_request > 0 ? ws->pair_cap_request : 24 * scap;  // first guess; refined from observed maxima
+    want = (want + 31) / 32 * 32;
+    if (ws->pairs && want == ws->pair_cap && ws->pair_groups == pot->max_groups) return PANTEA_OK;
+    if (ws->pairs) cudaFree(ws->pairs);
+    if (ws->pair_off) cudaFree(ws->pair_off);
+    ws->pairs = ws->pair_off = nullptr;
+    cudaError_t err = cudaMalloc((void**)&ws->pairs, sizeof(int32_t) * (size_t)ws->max_atoms * want);
+    if (err == cudaSuccess) err = cudaMalloc((void**)&ws->pair_off, sizeof(int32_t) * (size_t)ws->max_atoms * (pot->max_groups + 1));
+    if (err != cudaSuccess)
+        return fail(err == cudaErrorMemoryAllocation ? PANTEA_ENOMEM : PANTEA_ECUDA,
+                    std::string("pair-list allocation: ") + cudaGetErrorString(err));
+    ws->pair_cap = want;
+    ws->pair_groups = pot->max_groups;
+    return PANTEA_OK;
 }
 
 template <typename T>
 static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32_t* centres, int64_t n_centres, void* G,
                              void* dG, void* e_atom, void* forces, cudaStream_t st) {
     const pantea_potential* pot = ws->pot;
+    int rc = ensure_pair_storage(ws);
+    if (rc != PANTEA_OK) return rc;
     AtomArgs<T> a{};
     a.rec = (const Rec<T>*)ws->rec; a.nbr = ws->nbr; a.tcount = ws->nbr_tcount; a.cap = ws->cap;
+    a.scap = ws->smem_cap > 0 && ws->smem_cap < ws->cap ? ws->smem_cap : ws->cap; a.flags = ws->flags;
     a.slot_of = ws->slot_of; a.struct_of = ws->struct_of; a.boxes = ws->boxes;
     a.box = BoxArgK{ws->box[0], ws->box[1], ws->box[2], ws->has_box ? 1 : 0};
     double lmin = ws->box[0] < ws->box[1] ? ws->box[0] : ws->box[1];
     if (ws->box[2] < lmin) lmin = ws->box[2];
     a.wrap_jk = ws->boxes ? 1 : (ws->has_box && 0.5 * lmin < 2.0 * ws->rc * (1.0 + 1e-9) ? 1 : 0);
+    a.rc_list = ws->rc;
     a.tables = pot->dev; a.n_types = pot->n_elements; a.element_slot = element_slot;
     a.centres = centres;
     const bool energy_pass = (e_atom || forces) && !G && !dG;
     a.by_slot = energy_pass ? 1 : 0;
     a.n_work = energy_pass ? (int)ws->n : (int)n_centres;
     a.own_begin = (int)ws->own_begin; a.own_end = ws->own_end < 0 ? (int)ws->n : (int)ws->own_end;
+    a.pairs = ws->pairs; a.pair_off = ws->pair_off; a.pair_cap = ws->pair_cap; a.max_groups = pot->max_groups;
     a.G = (T*)G; a.dG = (T*)dG; a.e_atom = (T*)e_atom; a.forces = (T*)forces;
     a.counters = ws->counters;
     a.g_stride = element_slot >= 0 ? pot->host[element_slot].n_sf : pot->max_sf;
     a.n_cls_max = pot->max_cls; a.n_sf_max = pot->max_sf > 0 ? pot->max_sf : 1;
     a.n_neurons_max = pot->max_neurons; a.width_max = pot->max_width;
     if (a.n_work == 0) return PANTEA_OK;
+    if (a.n_work > ws->max_atoms) return fail(PANTEA_EINVAL, "more centres than the workspace capacity");
     if (g_num_sms == 0) {
         int dev = 0;
         PANTEA_CUDA_TRY(cudaGetDevice(&dev));
         PANTEA_CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
+    if (pot->max_groups > 0) {
+        rc = launch_filter<T>(a, st);
+        if (rc != PANTEA_OK) return rc;
+    }
     const bool grad = dG != nullptr || forces != nullptr;
     const int mm = pot->max_members;
     // few atoms: several warps per atom so that every SM sub-partition has work
     const bool wide = (int64_t)a.n_work < (int64_t)g_num_sms * 64;
-    if (wide) {
-        const size_t per_atom = atom_smem_bytes<T>(a.cap, a.n_cls_max, a.n_sf_max, a.n_neurons_max, a.width_max, 4);
-        return grad ? launch_mch<T, 4, true>(a, per_atom, mm, st) : launch_mch<T, 4, false>(a, per_atom, mm, st);
-    }
-    const size_t per_atom = atom_smem_bytes<T>(a.cap, a.n_cls_max, a.n_sf_max, a.n_neurons_max, a.width_max, 1);
-    return grad ? launch_mch<T, 1, true>(a, per_atom, mm, st) : launch_mch<T, 1, false>(a, per_atom, mm, st);
+    if (wide) return grad ? launch_mch<T, 4, true>(a, mm, st) : launch_mch<T, 4, false>(a, mm, st);
+    return grad ? launch_mch<T, 1, true>(a, mm, st) : launch_mch<T, 1, false>(a, mm, st);
 }
 
 int atom_kernel_launch(pantea_workspace* ws, int element_slot, const int32_t* centres, int64_t n_centres, void* G,

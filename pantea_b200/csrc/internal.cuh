@@ -91,7 +91,7 @@ struct ElementTable {
 struct pantea_potential {
     int n_elements = 0;
     double rc_max = 0.0;
-    int max_sf = 0, max_cls = 1, max_neurons = 0, max_width = 0, max_members = 1;
+    int max_sf = 0, max_cls = 1, max_neurons = 0, max_width = 0, max_members = 1, max_groups = 0;
     std::vector<pantea::ElementTable> host;
     pantea::ElementTable* dev = nullptr;  // [n_elements]
     std::vector<double*> dev_weights;
@@ -137,6 +137,9 @@ struct pantea_workspace {
     const pantea_potential* pot = nullptr;
     int64_t max_atoms = 0;
     int cap = 0;    // neighbours per row
+    int32_t* pairs = nullptr;      // [max_atoms][pair_cap] pre-filtered (j,k) pair lists
+    int32_t* pair_off = nullptr;   // [max_atoms][pair_groups + 1]
+    int pair_cap = 0, pair_groups = 0, pair_cap_request = 0;
     int smem_cap = 0;  // rows staged in shared memory by the atom kernel (0: cap); set from the observed maximum
     int dtype = PANTEA_F64;
     int n_types = 0;  // buckets used by the potential (others -> bucket n_types)

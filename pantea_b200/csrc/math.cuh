@@ -114,32 +114,36 @@ __device__ __forceinline__ double fast_sqrt(double a) {  // sqrt(a) for normal p
 }
 __device__ __forceinline__ float fast_sqrt(float a) { return __fsqrt_rn(a); }
 
-// exp(y) for y <= ~700, branch-free: magic-number range reduction, degree-12 polynomial on |f| <= ln2/2,
-// exponent patched in with integer arithmetic; results below ~1e-300 are returned as 0
-__device__ __forceinline__ double fast_exp(double y) {
-    const double shift = 6755399441055744.0;  // 1.5 * 2^52
-    const double yc = fmax(y, -690.0);
-    const double t = fma(yc, 1.4426950408889634, shift);
+// Taylor coefficients 1/n!, n = 0..12, in constant memory so that they fold into the FMA operands
+static __constant__ double kExpC[13] = {
+    1.0, 1.0, 0.5, 1.66666666666666666667e-01, 4.16666666666666666667e-02, 8.33333333333333333333e-03,
+    1.38888888888888888889e-03, 1.98412698412698412698e-04, 2.48015873015873015873e-05, 2.75573192239858906526e-06,
+    2.75573192239858906526e-07, 2.50521083854417187751e-08, 2.08767569878680989792e-09};
+static __constant__ double kExpK[4] = {1.4426950408889634, 6755399441055744.0 /* 1.5 * 2^52 */,
+                                       -6.93147180369123816490e-01, -1.90821492927058770002e-10};
+
+// exp(y), branch-free: magic-number range reduction, degree-12 polynomial on |f| <= ln2/2 (Estrin scheme for
+// instruction-level parallelism), exponent patched in with integer arithmetic.  CLAMP: arguments below -700 are
+// clamped (result ~1e-304 instead of 0/denormal); without CLAMP the caller guarantees -700 < y < 700.
+template <bool CLAMP>
+__device__ __forceinline__ double fast_exp_t(double y) {
+    const double yc = CLAMP ? fmax(y, -700.0) : y;
+    const double t = fma(yc, kExpK[0], kExpK[1]);
     const int k = __double2loint(t);
-    const double kf = t - shift;
-    double f = fma(kf, -6.93147180369123816490e-01, yc);
-    f = fma(kf, -1.90821492927058770002e-10, f);
-    double p = 2.08767569878680989792e-09;              // 1/12!
-    p = fma(p, f, 2.50521083854417187751e-08);          // 1/11!
-    p = fma(p, f, 2.75573192239858906526e-07);          // 1/10!
-    p = fma(p, f, 2.75573192239858906526e-06);          // 1/9!
-    p = fma(p, f, 2.48015873015873015873e-05);          // 1/8!
-    p = fma(p, f, 1.98412698412698412698e-04);          // 1/7!
-    p = fma(p, f, 1.38888888888888888889e-03);          // 1/6!
-    p = fma(p, f, 8.33333333333333333333e-03);          // 1/5!
-    p = fma(p, f, 4.16666666666666666667e-02);          // 1/4!
-    p = fma(p, f, 1.66666666666666666667e-01);          // 1/3!
-    p = fma(p, f, 0.5);
-    p = fma(p, f, 1.0);
-    p = fma(p, f, 1.0);
-    const double r = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-    return y < -690.0 ? 0.0 : r;
+    const double kf = t - kExpK[1];
+    double f = fma(kf, kExpK[2], yc);
+    f = fma(kf, kExpK[3], f);
+    const double f2 = f * f, f4 = f2 * f2, f8 = f4 * f4;
+    const double a0 = fma(kExpC[1], f, kExpC[0]), a1 = fma(kExpC[3], f, kExpC[2]), a2 = fma(kExpC[5], f, kExpC[4]),
+                 a3 = fma(kExpC[7], f, kExpC[6]), a4 = fma(kExpC[9], f, kExpC[8]), a5 = fma(kExpC[11], f, kExpC[10]);
+    const double b0 = fma(a1, f2, a0), b1 = fma(a3, f2, a2), b2 = fma(a5, f2, a4);
+    const double d0 = fma(b1, f4, b0), d1 = fma(kExpC[12], f4, b2);
+    const double p = fma(d1, f8, d0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
+__device__ __forceinline__ double fast_exp(double y) { return fast_exp_t<true>(y); }
+__device__ __forceinline__ double fast_exp_small(double y) { return fast_exp_t<false>(y); }
+__device__ __forceinline__ float fast_exp_small(float y) { return expf(y); }
 __device__ __forceinline__ float fast_exp(float y) { return expf(y); }
 
 __device__ __forceinline__ double cospi_t(double x) { return cospi(x); }
@@ -149,7 +153,7 @@ __device__ __forceinline__ float cospi_t(float x) { return cospif(x); }
 // tanh -> 0, i.e. where the cutoff function tanh^3 is itself negligible)
 template <typename T>
 __device__ __forceinline__ T fast_tanh_pos(T x) {
-    return (T)1 - (T)2 * fast_rcp(fast_exp((T)2 * x) + (T)1);
+    return (T)1 - (T)2 * fast_rcp(fast_exp_small((T)2 * x) + (T)1);
 }
 
 // cutoff value from the squared distance (third leg of G3), hot path

@@ -440,16 +440,31 @@ int pantea_neighbor_status(pantea_workspace* ws, int32_t* max_count, void* strea
     PANTEA_CUDA_TRY(cudaMemsetAsync(ws->flags, 0, 16, (cudaStream_t)stream));  // maxima are sticky until read
     PANTEA_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     if (max_count) *max_count = h[0];
-    if (h[1] > 0)
-        return fail(PANTEA_ECAPACITY, "neighbour block overflow in the atom kernel: " + std::to_string(h[1]) +
-                                          " neighbours > staged capacity " + std::to_string(ws->smem_cap));
-    if (h[0] <= ws->cap) {
-        // shared-memory footprint of the atom kernel follows the observed maximum (+10 % + 8 head-room)
-        int want = (h[0] + h[0] / 10 + 8 + 7) / 8 * 8;
+    int code = PANTEA_OK;
+    std::string msg;
+    if (h[1] > 0) {
+        code = PANTEA_ECAPACITY;
+        msg = "neighbour block overflow in the evaluation kernels: " + std::to_string(h[1]) + " neighbours > staged capacity " +
+              std::to_string(ws->smem_cap) + " (re-run: the capacity has been raised)";
+    }
+    const int seen = h[0] > h[1] ? h[0] : h[1];  // maxima since the last status call (0: nothing was built since)
+    if (seen > 0 && h[0] <= ws->cap) {
+        // shared-memory footprint of the evaluation kernels follows the observed maximum (+10 % + 8 head-room)
+        int want = (seen + seen / 10 + 8 + 7) / 8 * 8;
         if (want < 32) want = 32;
         if (want > ws->cap) want = ws->cap;
         if (want > ws->smem_cap || want < ws->smem_cap - 32) ws->smem_cap = want;
     }
+    if (h[2] > 0) {  // pair lists: capacity follows the observed maximum (+25 % head-room)
+        if (ws->pair_cap > 0 && h[2] > ws->pair_cap) {
+            code = PANTEA_ECAPACITY;
+            msg = "pair-list overflow: " + std::to_string(h[2]) + " pairs > capacity " + std::to_string(ws->pair_cap) +
+                  " (re-run: the capacity has been raised)";
+        }
+        const int want = h[2] + h[2] / 4 + 64;
+        if (want > ws->pair_cap || want < ws->pair_cap / 2) ws->pair_cap_request = want;
+    }
+    if (code != PANTEA_OK && h[0] <= ws->cap) return fail(code, msg);
     if (h[0] > ws->cap)
         return fail(PANTEA_ECAPACITY, "neighbour row overflow: " + std::to_string(h[0]) + " neighbours > capacity " +
                                           std::to_string(ws->cap));

@@ -156,6 +156,7 @@ int pantea_potential_create(const pantea_potential_desc* desc, pantea_potential*
         if (t.n_sf > pot->max_sf) pot->max_sf = t.n_sf;
         if (t.n_cls > pot->max_cls) pot->max_cls = t.n_cls;
         for (int g = 0; g < t.n_groups; ++g) if (t.groups[g].count > pot->max_members) pot->max_members = t.groups[g].count;
+        if (t.n_groups > pot->max_groups) pot->max_groups = t.n_groups;
         if (t.n_neurons > pot->max_neurons) pot->max_neurons = t.n_neurons;
         for (int l = 0; l <= t.n_layers; ++l)
             if (t.n_layers > 0 && t.sizes[l] > pot->max_width) pot->max_width = t.sizes[l];
@@ -240,7 +241,8 @@ int pantea_workspace_destroy(pantea_workspace* ws) {
     if (ws->md_graph) cudaGraphExecDestroy(ws->md_graph);
     if (ws->capture_stream) cudaStreamDestroy(ws->capture_stream);
     void* ptrs[] = {ws->rec, ws->slot_of, ws->struct_of, ws->nbr, ws->nbr_tcount, ws->cell_of, ws->tmp_order,
-                    ws->cell_start, ws->cell_fill, ws->flags, ws->e_partial, ws->md_forces, ws->md_eatom, ws->md_ke};
+                    ws->cell_start, ws->cell_fill, ws->flags, ws->e_partial, ws->md_forces, ws->md_eatom, ws->md_ke,
+                    ws->pairs, ws->pair_off};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete ws;

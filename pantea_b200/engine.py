@@ -257,6 +257,17 @@ class Workspace:
                                         _lib.stream_ptr()))
         return (r, d) if with_aux else r
 
+    def _checked(self, launch) -> None:
+        """Run `launch()` and verify (synchronising) that no device-side capacity was exceeded; the library raises
+        its capacities from the observed maxima, so an overflowing evaluation is simply repeated."""
+        lib = _lib.load()
+        for attempt in range(4):
+            launch()
+            code = lib.pantea_neighbor_status(self.handle, None, _lib.stream_ptr())
+            if code != _lib.PANTEA_ECAPACITY or attempt == 3:
+                _lib.check(code)
+                return
+
     def acsf(self, element_slot: int, n_symfunc: int, centres: Optional[torch.Tensor], values: bool, grad: bool):
         lib = _lib.load()
         dev = self._keep[0].device
@@ -266,8 +277,8 @@ class Workspace:
         G = torch.zeros((n_c, n_symfunc), dtype=self.dtype, device=dev) if values else None
         dG = torch.zeros((n_c, n_symfunc, 3), dtype=self.dtype, device=dev) if grad else None
         if n_c > 0 and n_symfunc > 0:
-            _lib.check(lib.pantea_acsf_compute(self.handle, element_slot, _lib.ptr(centres), n_c, _lib.ptr(G), _lib.ptr(dG),
-                                               _lib.stream_ptr()))
+            self._checked(lambda: _lib.check(lib.pantea_acsf_compute(
+                self.handle, element_slot, _lib.ptr(centres), n_c, _lib.ptr(G), _lib.ptr(dG), _lib.stream_ptr())))
         return G, dG
 
     def energy_forces(self, want_energy: bool = True, want_forces: bool = True, want_atomic: bool = False,
@@ -280,8 +291,8 @@ class Workspace:
         forces = None
         if want_forces:
             forces = out_forces if out_forces is not None else torch.zeros((n, 3), dtype=self.dtype, device=dev)
-        _lib.check(lib.pantea_energy_forces(self.handle, _lib.ptr(e_atom), _lib.ptr(forces), _lib.ptr(e_total), 0,
-                                            _lib.stream_ptr()))
+        self._checked(lambda: _lib.check(lib.pantea_energy_forces(
+            self.handle, _lib.ptr(e_atom), _lib.ptr(forces), _lib.ptr(e_total), 0, _lib.stream_ptr())))
         return e_total, e_atom, forces
 
 
