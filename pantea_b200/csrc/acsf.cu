@@ -70,6 +70,7 @@ struct AtomArgs {
     int g_stride;
     T* e_atom;
     T* forces;
+    T* gbuf;  // [n_work][n_sf_max][4] summed descriptors handed from the evaluation to the network kernel
     unsigned long long* counters;  // optional work counters: [0] pairs, [1] radial-SF evals, [2] triplet-SF evals
     int n_cls_max, n_sf_max, n_neurons_max, width_max;
 };
@@ -77,10 +78,8 @@ struct AtomArgs {
 template <typename T>
 __host__ __device__ inline size_t eval_smem_bytes(int cap, int n_cls, int n_sf, int n_neurons, int width, int wpa) {
     size_t t_elems = (size_t)(5 + 2 * n_cls) * cap   // neighbour block (structure of arrays)
-                     + (size_t)wpa * n_sf * 4        // per-warp partial sums
-                     + (size_t)(n_sf + n_neurons)    // layer activations
-                     + (size_t)n_neurons             // activation derivatives
-                     + 2 * (size_t)(width > n_sf ? width : n_sf);  // back-propagation ping-pong
+                     + (size_t)wpa * n_sf * 4;       // per-warp partial sums
+    (void)n_neurons; (void)width;
     return (t_elems * sizeof(T) + 15) & ~size_t(15);
 }
 
@@ -186,7 +185,9 @@ __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const At
         return;
     }
     const ElementTable& tab = a.tables[etype];
+    const int item_cap = a.scap * ((a.scap + 31) / 32);  // worst case: every neighbour pairs with every neighbour
     float4* sf4 = (float4*)smem_raw + (size_t)wib * a.scap;
+    int* items = (int*)(smem_raw + (size_t)kFilterWarps * a.scap * sizeof(float4)) + (size_t)wib * item_cap;
 
     Segments sg;
     sg.load(a.tcount + (size_t)slot * kBuckets, a.scap);
@@ -232,30 +233,51 @@ __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const At
         const float rc2f = grp.kind == PANTEA_G3 ? rcf * rcf * 1.0001f + 1e-4f : 3.0e38f;
         const int cls_bit = 1 << grp.cls;
         const int kbase = same ? bj : bk;
-        for (int aj = 0; aj < nj; ++aj) {  // neighbour j: uniform within the warp
-            const int j = bj + aj;
-            const float4 fj = sf4[j];
-            if (!(__float_as_int(fj.w) & cls_bit)) continue;  // beyond this group's cutoff
-            for (int kb = same ? aj + 1 : 0; kb < nk; kb += 64) {  // two 32-wide chunks of partners k per iteration
-                bool live[2];
+        // work items = (neighbour j, 32-wide chunk of partners k), enumerated j-major so that the pair order is
+        // deterministic; building the item list first lets every iteration below process two full items even when a
+        // neighbour has only a few partners left (triangular same-type loops)
+        int n_items = 0;
+        for (int j0 = 0; j0 < nj; j0 += 32) {
+            const int aj = j0 + lane;
+            const int start = same ? aj + 1 : 0;
+            int cnt = 0;
+            if (aj < nj && (__float_as_int(sf4[bj + aj].w) & cls_bit) && nk > start) cnt = (nk - start + 31) >> 5;
+            int incl = cnt;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int kk = kb + 32 * c + lane;
-                    const float4 fk = sf4[kbase + (kk < nk ? kk : 0)];
-                    float ex = fj.x - fk.x, ey = fj.y - fk.y, ez = fj.z - fk.z;
-                    if (wrap_jk) { ex = min_image(ex, flx); ey = min_image(ey, fly); ez = min_image(ez, flz); }
-                    const float d2 = ex * ex + ey * ey + ez * ez;
-                    live[c] = kk < nk && d2 < rc2f && (__float_as_int(fk.w) & cls_bit);
-                }
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(kFullMask, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const int base_i = n_items + incl - cnt;
+            for (int c = 0; c < cnt; ++c) items[base_i + c] = (bj + aj) | ((start + 32 * c) << 16);
+            n_items += __shfl_sync(kFullMask, incl, 31);
+        }
+        __syncwarp();
+        for (int it = 0; it < n_items; it += 2) {
+            const bool has1 = it + 1 < n_items;
+            const int item[2] = {items[it], items[has1 ? it + 1 : it]};
+            bool live[2];
+            int jk[2];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const unsigned mask = __ballot_sync(kFullMask, live[c]);
-                    const int pos = off + __popc(mask & lt_mask);
-                    if (live[c] && pos < a.pair_cap) list[pos] = j | ((kbase + kb + 32 * c + lane) << 16);
-                    off += __popc(mask);
-                }
+            for (int c = 0; c < 2; ++c) {
+                const int j = item[c] & 0xffff, kk = (item[c] >> 16) + lane;
+                const float4 fj = sf4[j];
+                const float4 fk = sf4[kbase + (kk < nk ? kk : 0)];
+                float ex = fj.x - fk.x, ey = fj.y - fk.y, ez = fj.z - fk.z;
+                if (wrap_jk) { ex = min_image(ex, flx); ey = min_image(ey, fly); ez = min_image(ez, flz); }
+                const float d2 = ex * ex + ey * ey + ez * ez;
+                live[c] = kk < nk && d2 < rc2f && (__float_as_int(fk.w) & cls_bit) && (c == 0 || has1);
+                jk[c] = j | ((kbase + kk) << 16);
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const unsigned mask = __ballot_sync(kFullMask, live[c]);
+                const int pos = off + __popc(mask & lt_mask);
+                if (live[c] && pos < a.pair_cap) list[pos] = jk[c];
+                off += __popc(mask);
             }
         }
+        __syncwarp();
     }
     if (lane == 0) {
         off_out[tab.n_groups] = off < a.pair_cap ? off : a.pair_cap;
@@ -414,13 +436,7 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
 
     int slot, out_row, etype;
     if (!resolve_item(a, w, slot, out_row, etype)) return;
-    if (etype >= a.n_types) {  // an atom no element network describes: contributes nothing
-        if (tid_atom == 0) {
-            if (a.e_atom) a.e_atom[out_row] = (T)0;
-            if (a.forces) { a.forces[3 * out_row] = (T)0; a.forces[3 * out_row + 1] = (T)0; a.forces[3 * out_row + 2] = (T)0; }
-        }
-        return;
-    }
+    if (etype >= a.n_types) return;  // an atom no element network describes (the network kernel writes zeros)
     const ElementTable& tab = a.tables[etype];
     const int n_sf = tab.n_sf;
     const Rec<T> ri = a.rec[slot];
@@ -441,11 +457,6 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
     T* sfc = sinv + cap;                          // [n_cls_max][cap]
     T* sdfc = sfc + (size_t)a.n_cls_max * cap;    // [n_cls_max][cap]
     T* sacc = sdfc + (size_t)a.n_cls_max * cap;   // [WPA][n_sf_max][4]
-    T* sh = sacc + (size_t)WPA * a.n_sf_max * 4;  // [n_sf_max + n_neurons_max]
-    T* sdact = sh + a.n_sf_max + a.n_neurons_max;
-    const int gw = a.width_max > a.n_sf_max ? a.width_max : a.n_sf_max;
-    T* sg0 = sdact + a.n_neurons_max;
-    T* sg1 = sg0 + gw;
 
     Segments sg;
     sg.load(a.tcount + (size_t)slot * kBuckets, cap);
@@ -564,67 +575,79 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
             const int s = e / 3, c = e - 3 * s;
             a.dG[((size_t)out_row * a.g_stride + s) * 3 + c] = sacc[4 * s + 1 + c];
         }
-    if (!a.e_atom && !a.forces) return;
-    if (tab.n_layers == 0) {
-        if (lane == 0) {
-            if (a.e_atom) a.e_atom[out_row] = (T)0;
-            if (a.forces) { a.forces[3 * out_row] = (T)0; a.forces[3 * out_row + 1] = (T)0; a.forces[3 * out_row + 2] = (T)0; }
-        }
-        return;
-    }
+    // hand the summed descriptor (value + central gradient) to the network kernel
+    if (a.gbuf)
+        for (int e = lane; e < n_sf * 4; e += 32) a.gbuf[(size_t)w * a.n_sf_max * 4 + e] = sacc[e];
+}
 
-    // ---- scaler + network forward --------------------------------------------------------------------
-    for (int s = lane; s < n_sf; s += 32)
-        sh[s] = (T)tab.offset[s] + (T)tab.slope[s] * (sacc[4 * s] - (T)tab.shift[s]);
-    __syncwarp();
-    const int L = tab.n_layers;
-    int in_off = 0, out_off = n_sf;
-    for (int l = 0; l < L; ++l) {
-        const int ni = tab.sizes[l], no = tab.sizes[l + 1];
-        const double* W = tab.weights + tab.w_off[l];
-        const double* B = W + (size_t)ni * no;
-        const int act = tab.acts[l];
-        for (int o = lane; o < no; o += 32) {
-            T z = (T)0;
-            for (int i = 0; i < ni; ++i) z += sh[in_off + i] * (T)W[(size_t)i * no + o];
-            z += (T)B[o];
-            T y, dy;
-            activation_eval_ool<T>(act, z, &y, &dy);
-            sh[out_off + o] = y;
-            sdact[out_off - n_sf + o] = dy;
-        }
-        __syncwarp();
-        in_off = out_off; out_off += no;
-    }
-    const T energy = sh[in_off];
-    if (lane == 0 && a.e_atom) a.e_atom[out_row] = energy;
-    if (!GRAD || !a.forces) return;
+// ------------------------------------------------------------------------------------------------
+// 3. scaler + per-element network forward / backward + force: one THREAD per atom (the networks are tiny:
+//    3-5-5-1 ... 30-25-25-1; a warp per atom would leave most lanes idle).  Per-thread scratch lives in shared
+//    memory, strided by thread.  Replaces scaler.py:206-246, model.py:53-58, energy.py:36-39, force.py:16-43.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMlpThreads = 64;
 
-    // ---- network backward: dE/dx~ -> dE/dG -> force ---------------------------------------------------
-    T* gc = sg0; T* gn = sg1;
-    if (lane == 0) gc[0] = (T)1;
-    __syncwarp();
-    int lay_out = out_off - tab.sizes[L];  // offset (in sh) of the outputs of layer l
-    for (int l = L - 1; l >= 0; --l) {
-        const int ni = tab.sizes[l], no = tab.sizes[l + 1];
-        const double* W = tab.weights + tab.w_off[l];
-        const T* da = sdact + (lay_out - n_sf);
-        for (int i = lane; i < ni; i += 32) {
-            T acc = (T)0;
-            for (int o = 0; o < no; ++o) acc += (T)W[(size_t)i * no + o] * (gc[o] * da[o]);
-            gn[i] = acc;
+template <typename T>
+__global__ void __launch_bounds__(kMlpThreads) mlp_force_kernel(const AtomArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int w = blockIdx.x * kMlpThreads + threadIdx.x;
+    if (w >= a.n_work) return;
+    int slot, out_row, etype;
+    if (!resolve_item(a, w, slot, out_row, etype)) return;
+    T energy = (T)0, fx = (T)0, fy = (T)0, fz = (T)0;
+    if (etype < a.n_types && a.tables[etype].n_layers > 0) {
+        const ElementTable& tab = a.tables[etype];
+        const int n_sf = tab.n_sf, L = tab.n_layers;
+        const T* g = a.gbuf + (size_t)w * a.n_sf_max * 4;
+        // per-thread scratch, element i of thread t at [i * kMlpThreads + t]
+        T* sh = (T*)smem_raw + threadIdx.x;                                       // [n_sf_max + n_neurons_max]
+        T* sdact = sh + (size_t)(a.n_sf_max + a.n_neurons_max) * kMlpThreads;       // [n_neurons_max]
+        const int gw = a.width_max > a.n_sf_max ? a.width_max : a.n_sf_max;
+        T* gc = sdact + (size_t)a.n_neurons_max * kMlpThreads;                      // [gw]
+        T* gn = gc + (size_t)gw * kMlpThreads;                                      // [gw]
+        for (int s = 0; s < n_sf; ++s)
+            sh[s * kMlpThreads] = (T)tab.offset[s] + (T)tab.slope[s] * (g[4 * s] - (T)tab.shift[s]);
+        int in_off = 0, out_off = n_sf;
+        for (int l = 0; l < L; ++l) {
+            const int ni = tab.sizes[l], no = tab.sizes[l + 1];
+            const double* W = tab.weights + tab.w_off[l];
+            const double* B = W + (size_t)ni * no;
+            const int act = tab.acts[l];
+            for (int o = 0; o < no; ++o) {
+                T z = (T)0;
+                for (int i = 0; i < ni; ++i) z += sh[(in_off + i) * kMlpThreads] * (T)W[(size_t)i * no + o];
+                z += (T)B[o];
+                T y, dy;
+                activation_eval_ool<T>(act, z, &y, &dy);
+                sh[(out_off + o) * kMlpThreads] = y;
+                sdact[(out_off - n_sf + o) * kMlpThreads] = dy;
+            }
+            in_off = out_off; out_off += no;
         }
-        __syncwarp();
-        T* tmp = gc; gc = gn; gn = tmp;
-        lay_out -= ni;
+        energy = sh[in_off * kMlpThreads];
+        if (a.forces) {
+            gc[0] = (T)1;
+            int lay_out = out_off - tab.sizes[L];  // offset (in sh) of the outputs of layer l
+            for (int l = L - 1; l >= 0; --l) {
+                const int ni = tab.sizes[l], no = tab.sizes[l + 1];
+                const double* W = tab.weights + tab.w_off[l];
+                const T* da = sdact + (size_t)(lay_out - n_sf) * kMlpThreads;
+                for (int i = 0; i < ni; ++i) {
+                    T acc = (T)0;
+                    for (int o = 0; o < no; ++o) acc += (T)W[(size_t)i * no + o] * (gc[o * kMlpThreads] * da[o * kMlpThreads]);
+                    gn[i * kMlpThreads] = acc;
+                }
+                T* tmp = gc; gc = gn; gn = tmp;
+                lay_out -= ni;
+            }
+            for (int s = 0; s < n_sf; ++s) {
+                const T ws_ = gc[s * kMlpThreads] * (T)tab.slope[s];
+                fx -= ws_ * g[4 * s + 1]; fy -= ws_ * g[4 * s + 2]; fz -= ws_ * g[4 * s + 3];
+            }
+        }
     }
-    T fx = 0, fy = 0, fz = 0;
-    for (int s = lane; s < n_sf; s += 32) {
-        const T ws_ = gc[s] * (T)tab.slope[s];
-        fx -= ws_ * sacc[4 * s + 1]; fy -= ws_ * sacc[4 * s + 2]; fz -= ws_ * sacc[4 * s + 3];
-    }
-    fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
-    if (lane == 0) { a.forces[3 * out_row] = fx; a.forces[3 * out_row + 1] = fy; a.forces[3 * out_row + 2] = fz; }
+    if (a.e_atom) a.e_atom[out_row] = energy;
+    if (a.forces) { a.forces[3 * out_row] = fx; a.forces[3 * out_row + 1] = fy; a.forces[3 * out_row + 2] = fz; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -709,7 +732,7 @@ static int launch_mch(const AtomArgs<T>& a, int max_members, cudaStream_t st) {
 
 template <typename T>
 static int launch_filter(const AtomArgs<T>& a, cudaStream_t st) {
-    const size_t smem = (size_t)kFilterWarps * a.scap * sizeof(float4);
+    const size_t smem = (size_t)kFilterWarps * a.scap * (sizeof(float4) + sizeof(int) * ((a.scap + 31) / 32));
     auto kern = pair_filter_kernel<T>;
     static size_t configured = 0;
     if (smem > configured) {
@@ -766,6 +789,15 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
     a.own_begin = (int)ws->own_begin; a.own_end = ws->own_end < 0 ? (int)ws->n : (int)ws->own_end;
     a.pairs = ws->pairs; a.pair_off = ws->pair_off; a.pair_cap = ws->pair_cap; a.max_groups = pot->max_groups;
     a.G = (T*)G; a.dG = (T*)dG; a.e_atom = (T*)e_atom; a.forces = (T*)forces;
+    a.gbuf = nullptr;
+    if (e_atom || forces) {
+        if (!ws->gbuf) {
+            const size_t bytes = sizeof(T) * (size_t)ws->max_atoms * (pot->max_sf > 0 ? pot->max_sf : 1) * 4;
+            cudaError_t err = cudaMalloc(&ws->gbuf, bytes);
+            if (err != cudaSuccess) return fail(PANTEA_ENOMEM, std::string("descriptor hand-off buffer: ") + cudaGetErrorString(err));
+        }
+        a.gbuf = (T*)ws->gbuf;
+    }
     a.counters = ws->counters;
     a.g_stride = element_slot >= 0 ? pot->host[element_slot].n_sf : pot->max_sf;
     a.n_cls_max = pot->max_cls; a.n_sf_max = pot->max_sf > 0 ? pot->max_sf : 1;
@@ -785,8 +817,23 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
     const int mm = pot->max_members;
     // few atoms: several warps per atom so that every SM sub-partition has work
     const bool wide = (int64_t)a.n_work < (int64_t)g_num_sms * 64;
-    if (wide) return grad ? launch_mch<T, 4, true>(a, mm, st) : launch_mch<T, 4, false>(a, mm, st);
-    return grad ? launch_mch<T, 1, true>(a, mm, st) : launch_mch<T, 1, false>(a, mm, st);
+    if (wide) rc = grad ? launch_mch<T, 4, true>(a, mm, st) : launch_mch<T, 4, false>(a, mm, st);
+    else rc = grad ? launch_mch<T, 1, true>(a, mm, st) : launch_mch<T, 1, false>(a, mm, st);
+    if (rc != PANTEA_OK || !a.gbuf) return rc;
+    {
+        const int gw = a.width_max > a.n_sf_max ? a.width_max : a.n_sf_max;
+        const size_t smem = (size_t)(a.n_sf_max + 2 * a.n_neurons_max + 2 * gw) * kMlpThreads * sizeof(T);
+        auto kern = mlp_force_kernel<T>;
+        static size_t configured = 0;
+        if (smem > configured) {
+            if (smem > 227 * 1024) return fail(PANTEA_EINVAL, "network too wide for the per-thread shared-memory scratch");
+            PANTEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        kern<<<(a.n_work + kMlpThreads - 1) / kMlpThreads, kMlpThreads, smem, st>>>(a);
+        PANTEA_LAUNCH_CHECK();
+    }
+    return PANTEA_OK;
 }
 
 int atom_kernel_launch(pantea_workspace* ws, int element_slot, const int32_t* centres, int64_t n_centres, void* G,

@@ -137,6 +137,7 @@ struct pantea_workspace {
     const pantea_potential* pot = nullptr;
     int64_t max_atoms = 0;
     int cap = 0;    // neighbours per row
+    void* gbuf = nullptr;          // [max_atoms][max_sf][4] summed descriptors (evaluation -> network kernel)
     int32_t* pairs = nullptr;      // [max_atoms][pair_cap] pre-filtered (j,k) pair lists
     int32_t* pair_off = nullptr;   // [max_atoms][pair_groups + 1]
     int pair_cap = 0, pair_groups = 0, pair_cap_request = 0;
