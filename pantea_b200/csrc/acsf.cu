@@ -300,7 +300,7 @@ template <typename T, int WPA, bool GRAD, int MCH, bool FAST>
 __device__ __forceinline__ void angular_group(const ElementTable& tab, const AngularGroup& grp, int m0, int mc,
                                               const NbrBlock<T>& nb, const int32_t* __restrict__ list, int count,
                                               bool wrap_jk, T lx, T ly, T lz, int lane, int tid_atom, T* my_acc,
-                                              unsigned long long& cnt_trip) {
+                                              const T* __restrict__ etab, unsigned long long& cnt_trip) {
     constexpr int NU = kNU;
     constexpr int S = 32 * WPA;
     const int ctype = tab.cls[grp.cls].type;
@@ -353,7 +353,7 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
 #pragma unroll
             for (int u = 0; u < NU; ++u) rjk[u] = fast_sqrt(valid[u] ? rjk2[u] : (T)1);
 #pragma unroll
-            for (int u = 0; u < NU; ++u) t[u] = fast_tanh_pos<T>((T)1 - rjk[u] * inv_rc);
+            for (int u = 0; u < NU; ++u) t[u] = fast_tanh_pos_tab<T>((T)1 - rjk[u] * inv_rc, etab);
 #pragma unroll
             for (int u = 0; u < NU; ++u) {
                 fcjk[u] = (valid[u] && rjk[u] < rc) ? t[u] * t[u] * t[u] : (T)0;
@@ -383,7 +383,7 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
             if (MCH == 1 || m < mc) {
                 T e[NU];
 #pragma unroll
-                for (int u = 0; u < NU; ++u) e[u] = fast_exp(m_neta[m] * r2[u]);
+                for (int u = 0; u < NU; ++u) e[u] = fast_exp_tab<true>(m_neta[m] * r2[u], etab);
 #pragma unroll
                 for (int u = 0; u < NU; ++u) {
                     const T bs = (T)1 + m_lam[m] * cost[u];
@@ -431,6 +431,9 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
     const int wrank = WPA == 1 ? 0 : wib;           // rank of this warp among the atom's warps
     const int tid_atom = wrank * 32 + lane;         // thread index within the atom group
     constexpr int S = 32 * WPA;                     // threads per atom
+    __shared__ T s_etab[64];                        // 2^(i/64) for the table-driven exponential
+    exp2_table_fill(s_etab, threadIdx.x, blockDim.x);
+    __syncthreads();
     const int w = blockIdx.x * (WPA == 1 ? kAtomsPerBlock : 1) + atom_in_block;
     if (w >= a.n_work) return;
 
@@ -540,10 +543,10 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
                 const int mc = grp.count - m0 < MCH ? grp.count - m0 : MCH;
                 if (fast)
                     angular_group<T, WPA, GRAD, MCH, true>(tab, grp, m0, mc, nb, lists + lo, count, wrap_jk, lx, ly, lz, lane,
-                                                           tid_atom, my_acc, cnt_trip);
+                                                           tid_atom, my_acc, s_etab, cnt_trip);
                 else
                     angular_group<T, WPA, GRAD, MCH, false>(tab, grp, m0, mc, nb, lists + lo, count, wrap_jk, lx, ly, lz, lane,
-                                                            tid_atom, my_acc, cnt_trip);
+                                                            tid_atom, my_acc, s_etab, cnt_trip);
             }
         }
     }

@@ -141,6 +141,40 @@ __device__ __forceinline__ double fast_exp_t(double y) {
     const double p = fma(d1, f8, d0);
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
+// Table-driven exp for the triplet loop: exp(y) = 2^k * T[i] * p(f) with n = round(y * 64/ln2) = 64 k + i,
+// f = y - n ln2/64 (|f| <= ln2/128) and a degree-5 polynomial; T[i] = 2^(i/64) lives in shared memory
+// (`exp2_table_fill`).  ~10 FP64 instructions instead of ~18; arguments below -700 are clamped.
+static __constant__ double kExpT[6] = {92.332482616893657 /* 64/ln2 */, 6755399441055744.0 /* 1.5 * 2^52 */,
+                                       -6.93147180369123816490e-01 / 64.0, -1.90821492927058770002e-10 / 64.0,
+                                       1.66666666666666666667e-01, 4.16666666666666666667e-02};
+__device__ __forceinline__ void exp2_table_fill(double* tab, int tid, int nthreads) {
+    for (int i = tid; i < 64; i += nthreads) tab[i] = exp2((double)i * (1.0 / 64.0));
+}
+__device__ __forceinline__ void exp2_table_fill(float*, int, int) {}
+template <bool CLAMP>
+__device__ __forceinline__ double fast_exp_tab(double y, const double* __restrict__ tab) {
+    const double yc = CLAMP ? fmax(y, -700.0) : y;
+    const double t = fma(yc, kExpT[0], kExpT[1]);
+    const int n = __double2loint(t);
+    const double nf = t - kExpT[1];
+    double f = fma(nf, kExpT[2], yc);
+    f = fma(nf, kExpT[3], f);
+    double p = fma(8.33333333333333333333e-03, f, kExpT[5]);
+    p = fma(p, f, kExpT[4]);
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    p *= tab[n & 63];
+    return __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
+}
+template <bool CLAMP>
+__device__ __forceinline__ float fast_exp_tab(float y, const float*) { return expf(y); }
+// tanh(x), x in [0, ~20], through the table-driven exponential
+template <typename T>
+__device__ __forceinline__ T fast_tanh_pos_tab(T x, const T* __restrict__ tab) {
+    return (T)1 - (T)2 * fast_rcp(fast_exp_tab<false>((T)2 * x, tab) + (T)1);
+}
+
 __device__ __forceinline__ double fast_exp(double y) { return fast_exp_t<true>(y); }
 __device__ __forceinline__ double fast_exp_small(double y) { return fast_exp_t<false>(y); }
 __device__ __forceinline__ float fast_exp_small(float y) { return expf(y); }
