@@ -10,7 +10,7 @@
 //     whose r_jk^2 lies below a slightly inclusive single-precision bound.  Survivors are ballot-compacted into a
 //     per-atom pair list in global memory (coalesced 4-byte stores, deterministic order).
 //  2. `hdnnp_eval_kernel` (FP64 / FP32 arithmetic pipe).  WPA warps per central atom stage the full-precision
-//     neighbour block (d_ij, r_ij, 1/r_ij, fc, fc' per cutoff class; structure-of-arrays) in shared memory,
+//     neighbour block (records d_ij, r_ij, 1/r_ij, fc, fc' per cutoff class) in shared memory,
 //     evaluate the radial functions (lanes over neighbours) and walk the pair lists flat: every lane evaluates NU
 //     independent triplets per iteration (r_jk recomputed exactly; the reference's r_jk > 0 and r_jk < rc tests are
 //     applied here), so the ~100-FP64-instruction triplet body runs with full warps and NU independent dependency
@@ -77,7 +77,7 @@ struct AtomArgs {
 
 template <typename T>
 __host__ __device__ inline size_t eval_smem_bytes(int cap, int n_cls, int n_sf, int n_neurons, int width, int wpa) {
-    size_t t_elems = (size_t)(5 + 2 * n_cls) * cap   // neighbour block (structure of arrays)
+    size_t t_elems = (size_t)(5 + 2 * n_cls) * cap   // neighbour records
                      + (size_t)wpa * n_sf * 4;       // per-warp partial sums
     (void)n_neurons; (void)width;
     return (t_elems * sizeof(T) + 15) & ~size_t(15);
@@ -288,9 +288,13 @@ __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const At
 // ------------------------------------------------------------------------------------------------
 // 2. evaluation
 // ------------------------------------------------------------------------------------------------
+// staged neighbour block: array of records [dx, dy, dz, r, 1/r, (fc, fc') per cutoff class]; the record length
+// 5 + 2 n_cls is odd, so consecutive as well as scattered records spread over the shared-memory banks, and one
+// address computation per neighbour serves all of its fields
 template <typename T>
 struct NbrBlock {
-    const T *dx, *dy, *dz, *r, *inv, *fc, *dfc;  // fc / dfc already offset to the group's cutoff class
+    const T* rec;
+    int stride, fco;  // record length; offset of (fc, fc') of the group's cutoff class
 };
 
 // One angular group (same neighbour types, cutoff and kind), members [m0, m0 + mc), flat over the pair list.
@@ -335,9 +339,11 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
 #pragma unroll
         for (int u = 0; u < NU; ++u) {
             const int j = jk[u] & 0xffff, k = jk[u] >> 16;
-            dxj[u] = nb.dx[j]; dyj[u] = nb.dy[j]; dzj[u] = nb.dz[j]; rj[u] = nb.r[j]; ivj[u] = nb.inv[j]; fcj[u] = nb.fc[j];
-            dxk[u] = nb.dx[k]; dyk[u] = nb.dy[k]; dzk[u] = nb.dz[k]; rk[u] = nb.r[k]; ivk[u] = nb.inv[k]; fck[u] = nb.fc[k];
-            dfj[u] = GRAD ? nb.dfc[j] : (T)0; dfk[u] = GRAD ? nb.dfc[k] : (T)0;
+            const T* pj = nb.rec + j * nb.stride;
+            const T* pk = nb.rec + k * nb.stride;
+            dxj[u] = pj[0]; dyj[u] = pj[1]; dzj[u] = pj[2]; rj[u] = pj[3]; ivj[u] = pj[4]; fcj[u] = pj[nb.fco];
+            dxk[u] = pk[0]; dyk[u] = pk[1]; dzk[u] = pk[2]; rk[u] = pk[3]; ivk[u] = pk[4]; fck[u] = pk[nb.fco];
+            dfj[u] = GRAD ? pj[nb.fco + 1] : (T)0; dfk[u] = GRAD ? pk[nb.fco + 1] : (T)0;
         }
 #pragma unroll
         for (int u = 0; u < NU; ++u) {  // r_jk = |pbc(d_ij - d_ik)| (reference acsf.py:316-320), exact
@@ -452,14 +458,9 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
     // ---- carve shared memory ---------------------------------------------------------------------
     const int cap = a.scap;
     const size_t per_atom = eval_smem_bytes<T>(cap, a.n_cls_max, a.n_sf_max, a.n_neurons_max, a.width_max, WPA);
-    T* sdx = (T*)(smem_raw + (size_t)atom_in_block * per_atom);
-    T* sdy = sdx + cap;
-    T* sdz = sdy + cap;
-    T* sr = sdz + cap;
-    T* sinv = sr + cap;
-    T* sfc = sinv + cap;                          // [n_cls_max][cap]
-    T* sdfc = sfc + (size_t)a.n_cls_max * cap;    // [n_cls_max][cap]
-    T* sacc = sdfc + (size_t)a.n_cls_max * cap;   // [WPA][n_sf_max][4]
+    const int stride = 5 + 2 * a.n_cls_max;
+    T* snb = (T*)(smem_raw + (size_t)atom_in_block * per_atom);  // [cap][stride] neighbour records
+    T* sacc = snb + (size_t)stride * cap;                        // [WPA][n_sf_max][4]
 
     Segments sg;
     sg.load(a.tcount + (size_t)slot * kBuckets, cap);
@@ -482,7 +483,8 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
                 T dx = sub_rn(ri.x, rj.x), dy = sub_rn(ri.y, rj.y), dz = sub_rn(ri.z, rj.z);
                 if (pbc) { dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz); }
                 const T r = norm3_rn(dx, dy, dz);
-                sdx[n] = dx; sdy[n] = dy; sdz[n] = dz; sr[n] = r; sinv[n] = (T)1 / r;
+                T* p = snb + (size_t)n * stride;
+                p[0] = dx; p[1] = dy; p[2] = dz; p[3] = r; p[4] = (T)1 / r;
                 for (int c = 0; c < n_cls; ++c) {
                     T fc, dfc;
                     const int ct = tab.cls[c].type;
@@ -494,7 +496,7 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
                     } else {
                         cutoff_eval_ool<T>(ct, r, rcc, &fc, &dfc);
                     }
-                    sfc[c * cap + n] = fc; sdfc[c * cap + n] = dfc;
+                    p[5 + 2 * c] = fc; p[6 + 2 * c] = dfc;
                 }
             }
         }
@@ -509,11 +511,11 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
         const RadialSF sf = tab.radial[s];
         const int lo = sg.lo(sf.type_j), hi = sg.hi(sf.type_j);
         const T eta = (T)sf.eta, rs = (T)sf.r_shift;
-        const T* fcv = sfc + sf.cls * cap;
-        const T* dfcv = sdfc + sf.cls * cap;
+        const int fco = 5 + 2 * sf.cls;
         T g = 0, gx = 0, gy = 0, gz = 0;
         for (int n = lo + tid_atom; n < hi; n += S) {
-            const T r = sr[n], fc = fcv[n], dfc = dfcv[n];
+            const T* p = snb + (size_t)n * stride;
+            const T r = p[3], fc = p[fco], dfc = p[fco + 1];
             T val, dval;
             if (sf.kind == PANTEA_G1) { val = fc; dval = dfc; }
             else {
@@ -522,7 +524,7 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
             }
             g += val;
             ++cnt_rad;
-            if (GRAD) { const T sc = dval * sinv[n]; gx += sc * sdx[n]; gy += sc * sdy[n]; gz += sc * sdz[n]; }
+            if (GRAD) { const T sc = dval * p[4]; gx += sc * p[0]; gy += sc * p[1]; gz += sc * p[2]; }
         }
         g = warp_sum(g);
         if (GRAD) { gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz); }
@@ -536,7 +538,7 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
         for (int gi = 0; gi < tab.n_groups; ++gi) {
             const AngularGroup grp = tab.groups[gi];
             const int lo = offs[gi], count = offs[gi + 1] - lo;
-            NbrBlock<T> nb{sdx, sdy, sdz, sr, sinv, sfc + grp.cls * cap, sdfc + grp.cls * cap};
+            NbrBlock<T> nb{snb, stride, 5 + 2 * grp.cls};
             bool fast = tab.cls[grp.cls].type == PANTEA_CUT_TANHU && grp.kind == PANTEA_G3;
             for (int m = 0; m < grp.count; ++m) fast = fast && tab.members[grp.first + m].izeta == 1;
             for (int m0 = 0; m0 < grp.count; m0 += MCH) {

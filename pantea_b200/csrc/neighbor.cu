@@ -186,6 +186,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) neighbor_rows_kernel(cons
         if (a.boxes) { lx = (T)a.boxes[3 * s]; ly = (T)a.boxes[3 * s + 1]; lz = (T)a.boxes[3 * s + 2]; pbc = true; }
     }
     const T rc = (T)a.rc;
+    const T rel = sizeof(T) == 8 ? (T)1e-12 : (T)1e-5;
+    const T rc2_lo = rc * rc * ((T)1 - rel), rc2_hi = rc * rc * ((T)1 + rel);
     int cnt = 0;
 
     auto scan = [&](int lo, int hi) {
@@ -197,8 +199,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) neighbor_rows_kernel(cons
                 Rec<T> rj = rec[j];
                 T dx = sub_rn(ri.x, rj.x), dy = sub_rn(ri.y, rj.y), dz = sub_rn(ri.z, rj.z);
                 if (pbc) { dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz); }
-                T r = norm3_rn(dx, dy, dz);
-                ok = (r <= rc) && (r > (T)0);
+                // predicate (r <= rc) & (r > 0) on r = sqrt((dx^2 + dy^2) + dz^2): the correctly rounded root is only
+                // needed when r^2 is within rounding distance of rc^2
+                const T r2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
+                if (r2 < rc2_lo) ok = r2 > (T)0;
+                else if (r2 > rc2_hi) ok = false;
+                else { const T r = norm3_rn(dx, dy, dz); ok = (r <= rc) && (r > (T)0); }
                 bucket = rec_type(rj);
             }
             unsigned m = __ballot_sync(kFull, ok);
