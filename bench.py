@@ -42,7 +42,7 @@ FLOP_MLP = {1: 540.0, 2: 580.0}  # H, O networks of h2o.json (forward + input gr
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--atoms", type=int, default=int(os.environ.get("PANTEA_BENCH_ATOMS", "100000")))
@@ -70,7 +70,7 @@ class ClockSampler:
         self.index = device_index
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(device_index)], stdout=subprocess.PIPE,
+                                          "-lms", "100", "-i", str(device_index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -265,11 +265,12 @@ def run_b200(args) -> None:
         tfile = ROOT / "profiles" / "traffic.json"
         if tfile.exists():
             try:
-                traffic = json.loads(tfile.read_text()).get("hdnnp_atom_kernel_dram_bytes_per_launch")
+                traffic = json.loads(tfile.read_text()).get("force_eval_dram_bytes_per_launch")
             except (ValueError, OSError):
                 traffic = None
         roofline = {"bound": "fp64_pipe" if dtype == torch.float64 else "fp32_pipe",
-                    "kernel": "hdnnp_atom_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "kernel": "force evaluation = pair_filter_kernel + hdnnp_eval_kernel (dominant, ~74 %) + mlp_force_kernel",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak if peak else None, "traffic": traffic,
                     "peak_source": "measured live: FMA microbenchmark (pantea_bench_fma), CUDA-core pipe",
                     "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops_kernel,
