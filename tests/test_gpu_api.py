@@ -1,0 +1,192 @@
+"""The reference's own API-level tests, re-stated against pantea_b200's mirror of that API (GPU).
+
+Mirrors /root/reference/tests/test_acsf.py, test_nnp.py, test_md.py (API behaviour) and the notebook cells whose
+printed outputs serve as golden vectors; the numbers come from tests/golden/reference_vectors.json."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vec(golden_dir):
+    return json.loads((golden_dir / "reference_vectors.json").read_text())
+
+
+@pytest.fixture(scope="module")
+def h2o_structure(golden_dir):
+    from pantea_b200.datasets import Dataset
+    return Dataset.from_runner(golden_dir / "h2o.data")[0]
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def test_acsf_without_pbc(vec):
+    """reference tests/test_acsf.py:123-151"""
+    from pantea_b200.atoms import Structure
+    from pantea_b200.descriptors.acsf import ACSF, G2, CutoffFunction, NeighborElements
+    v = vec["ne2_g2"]
+    cfn = CutoffFunction.from_type("tanhu", r_cutoff=3.0)
+    acsf = ACSF("Ne", tuple((G2(cfn, eta=1.0, r_shift=rs), NeighborElements("Ne")) for rs in v["r_shifts"]), ())
+    s = Structure.from_dict({"positions": v["positions"], "elements": v["elements"]})
+    out = acsf(s)
+    assert tuple(out.shape) == (2, 5)
+    np.testing.assert_allclose(_np(out), np.tile(v["expected_row"], (2, 1)), rtol=1e-8)
+
+
+def test_acsf_with_pbc_and_index_validation(vec, h2o_structure):
+    """reference tests/test_acsf.py:153-173 and acsf.py:66-80, 103-113"""
+    from pantea_b200.descriptors.acsf import ACSF, G2, G3, CutoffFunction, NeighborElements
+    v = vec["h2o_pbc_g2_g3"]
+    cfn = CutoffFunction.from_type("tanhu", r_cutoff=v["cutoff"][1])
+    acsf = ACSF("O", ((G2(cfn, r_shift=0.0, eta=0.001), NeighborElements("H")),),
+                ((G3(cfn, eta=0.07, zeta=1.0, lambda0=1.0, r_shift=0.0), NeighborElements("H", "H")),))
+    assert tuple(acsf(h2o_structure).shape) == tuple(v["shape"])
+    np.testing.assert_allclose(_np(acsf(h2o_structure, atom_index=0)), [v["expected_atom0"]], rtol=0, atol=6e-11)
+    with pytest.raises(ValueError):
+        acsf(h2o_structure, atom_index=1)             # atom 1 is H, the descriptor is O-centred
+    with pytest.raises(ValueError):
+        acsf.grad(h2o_structure, atom_index=12)       # out of range
+    assert tuple(acsf.grad(h2o_structure).shape) == (12, 2, 3)          # all atoms when atom_index is None
+    assert tuple(acsf.grad(h2o_structure, atom_index=[0, 3]).shape) == (2, 2, 3)
+
+
+def test_notebook_descriptor_values_gradient_distances_neighbors(vec, h2o_structure):
+    """examples/getting_started.ipynb cells 17, 20, 25-29"""
+    from pantea_b200.atoms import Neighbor, calculate_distances
+    from pantea_b200.descriptors.acsf import ACSF, G2, G3, CutoffFunction, NeighborElements
+    cfn = CutoffFunction.from_type("tanhu", r_cutoff=12.0)
+    acsf = ACSF("O", ((G2(cfn, 0.0, 0.001), NeighborElements("H")), (G2(cfn, 0.0, 0.01), NeighborElements("H"))),
+                ((G3(cfn, 0.2, 1.0, 1.0, 0.0), NeighborElements("H", "H")), (G3(cfn, 0.2, 1.0, 1.0, 0.0), NeighborElements("H", "O"))))
+    v = vec["notebook_acsf"]
+    np.testing.assert_allclose(_np(acsf(h2o_structure)), v["expected_values"], rtol=2e-8)
+    np.testing.assert_allclose(_np(acsf.grad(h2o_structure)[:1])[0], v["expected_grad_atom0"], atol=6e-9)
+    d = calculate_distances(h2o_structure)
+    np.testing.assert_allclose(_np(d[0, :5]), vec["notebook_distances"]["expected"], atol=5e-9)
+    d2, dx = calculate_distances(h2o_structure, atom_index=[0, 1], neighbor_atom_index=[2, 3, 4], with_aux=True)
+    assert tuple(d2.shape) == (2, 3) and tuple(dx.shape) == (2, 3, 3)
+    np.testing.assert_allclose(_np(d2), _np(d[:2, 2:5]), rtol=0, atol=0)
+    nb = Neighbor.from_structure(h2o_structure, r_cutoff=vec["notebook_neighbors"]["r_cutoff"])
+    assert int(nb.masks[0].sum()) == vec["notebook_neighbors"]["expected_count_atom0"]
+    assert nb.masks.shape == (12, 12) and not bool(nb.masks.diagonal().any())
+    assert repr(nb) == "Neighbor(r_cutoff=10.0)"
+
+
+@pytest.mark.parametrize("dtype,e_atol,f_rtol", [(torch.float64, 3e-7, 1e-5), (torch.float32, 1e-6, 3e-5)])
+def test_nnp_outputs(vec, golden_dir, dtype, e_atol, f_rtol):
+    """reference tests/test_nnp.py:44-81 (its FLOATX is float32; both modes are checked here)"""
+    from pantea_b200.datasets import Dataset
+    from pantea_b200.potentials import NeuralNetworkPotential
+    from pantea_b200.types import default_dtype
+    old = default_dtype.FLOATX
+    default_dtype.FLOATX = dtype
+    try:
+        nnp = NeuralNetworkPotential.from_runner(golden_dir / "h2o.json")
+        assert nnp.num_elements == 2 and nnp.elements == ("H", "O")
+        structure = Dataset.from_runner(golden_dir / "h2o.data")[0]
+        with pytest.raises(ValueError):
+            nnp(structure)                                   # scaler parameters not loaded yet
+        nnp.load_scaler()
+        nnp.load_model()
+        v = vec["nnp_fp32"]
+        energy, forces = nnp(structure), nnp.compute_forces(structure)
+        assert energy.ndim == 0 and tuple(forces.shape) == (12, 3) and forces.dtype == dtype
+        np.testing.assert_allclose(float(energy), v["energy"], rtol=0, atol=e_atol)
+        np.testing.assert_allclose(_np(forces).astype(np.float64), v["forces"], rtol=f_rtol, atol=2e-7)
+        e2, f2 = nnp.compute_energy_and_forces(structure)
+        assert float(e2) == float(energy) and torch.equal(f2, forces)
+    finally:
+        default_dtype.FLOATX = old
+
+
+def test_structure_missing_element_raises(golden_dir):
+    from pantea_b200.atoms import Structure
+    from pantea_b200.potentials import NeuralNetworkPotential
+    nnp = NeuralNetworkPotential.from_runner(golden_dir / "h2o.json")
+    nnp.load()
+    only_o = Structure.from_dict({"positions": [[0.0, 0, 0], [3.0, 0, 0]], "elements": ["O", "O"],
+                                  "lattice": np.diag([30.0, 30.0, 30.0])})
+    with pytest.raises(KeyError):
+        nnp(only_o)                                           # reference: positions['H'] KeyError (energy.py:54-60)
+
+
+def _water_system(n_atoms=192, temperature=300.0):
+    from pantea_b200.atoms import Structure
+    from pantea_b200.potentials import NeuralNetworkPotential
+    from pantea_b200.simulation import System
+    from pantea_b200.utils.synthetic import water_box
+    from tests.conftest import GOLDEN
+    nnp = NeuralNetworkPotential.from_runner(GOLDEN / "h2o.json")
+    nnp.load()
+    p, t, box = water_box(n_atoms)
+    s = Structure.from_dict({"positions": p, "elements": ["H" if x == 1 else "O" for x in t], "lattice": np.diag(box)})
+    return System.from_structure(s, nnp, temperature=temperature, seed=2024), nnp
+
+
+def test_md_simulator_api_and_device_loop_agree():
+    """reference tests/test_md.py:99-126 (step counter, elapsed time, COM velocity) + one-step vs device-loop equality"""
+    from pantea_b200.simulation import MDSimulator, simulate
+    from pantea_b200.units import units
+    sys_a, _ = _water_system()
+    sys_b, _ = _water_system()
+    assert abs(float(sys_a.get_temperature()) - 300.0) < 1e-9
+    np.testing.assert_allclose(_np(sys_a.get_center_of_mass_velocity()), 0.0, atol=1e-12)
+    md_a, md_b = MDSimulator(time_step=0.25), MDSimulator(time_step=0.25)
+    for _ in range(3):
+        md_a.simulate_one_step(sys_a)
+    md_b.simulate_steps(sys_b, 3)
+    assert md_a.step == md_b.step == 3 and md_a.elapsed_time == pytest.approx(0.75)
+    assert torch.equal(sys_a.positions, sys_b.positions) and torch.equal(sys_a.velocities, sys_b.velocities)
+    assert torch.equal(sys_a.forces, sys_b.forces)
+    line = md_a.repr_physical_params(sys_a)
+    assert line.startswith("3 ") and "Temp[K]:" in line and "Etot[Ha]:" in line and "Pres[kb]:" in line
+    assert float(sys_a.get_total_energy()) == pytest.approx(float(sys_a.get_potential_energy()) + float(sys_a.get_kinetic_energy()))
+    simulate(sys_b, md_b, num_steps=4, output_freq=2)
+    assert md_b.step == 7
+    assert units.TO_PICO_SECOND * md_b.elapsed_time == pytest.approx(units.TO_PICO_SECOND * 1.75)
+
+
+def test_thermostat_pulls_temperature_towards_target():
+    from pantea_b200.simulation import BrendsenThermostat, MDSimulator
+    system, _ = _water_system(temperature=600.0)
+    md = MDSimulator(time_step=0.25, thermostat=BrendsenThermostat(target_temperature=300.0, time_constant=2.5))
+    t0 = float(system.get_temperature())
+    v_before = system.velocities.clone()
+    scaled = md.thermostat.get_rescaled_velocities(md, system)
+    factor = 1.0 / np.sqrt(1.0 + (0.25 / 2.5) * (t0 / 300.0 - 1.0))           # thermostat.py:16-21
+    np.testing.assert_allclose(_np(scaled), _np(v_before) * factor, rtol=1e-13)
+    sys_loop, _ = _water_system(temperature=600.0)
+    md_loop = MDSimulator(time_step=0.25, thermostat=BrendsenThermostat(300.0, 2.5))
+    md.simulate_one_step(system)
+    md_loop.simulate_steps(sys_loop, 1)
+    np.testing.assert_allclose(_np(system.velocities), _np(sys_loop.velocities), rtol=1e-12, atol=1e-15)
+
+
+def test_mc_simulator_follows_numpy_stream():
+    """reference monte_carlo.py:65-91: displacements, indices, then the acceptance draw from numpy's global stream"""
+    from pantea_b200.simulation import MCSimulator
+    system, nnp = _water_system(n_atoms=24)
+    e0 = float(system.structure.total_energy)
+    pos0 = system.positions.clone()
+    mc = MCSimulator(translate_step=0.05, target_temperature=300.0, movements_per_step=3, seed=12345)
+    rng = np.random.RandomState(12345)
+    disp = rng.uniform(-0.05, 0.05, size=(3, 3))
+    idx = rng.randint(0, system.natoms, size=(3,))
+    mc.simulate_one_step(system)
+    assert mc.step == 1
+    trial = pos0.clone()
+    trial.index_add_(0, torch.as_tensor(idx, device=trial.device), torch.as_tensor(disp, device=trial.device))
+    e_trial = float(nnp(system.structure.replace(positions=trial)))
+    if e_trial <= e0:
+        accepted = True
+    else:
+        accepted = np.exp(-(e_trial - e0) / (3.166811563e-6 * 300.0)) >= rng.uniform(0.0, 1.0)
+    expected = system.structure.replace(positions=trial).positions if accepted else pos0
+    assert torch.equal(system.positions, expected)
+    assert float(system.structure.total_energy) == pytest.approx(e_trial if accepted else e0)
+    assert mc.repr_physical_params(system).startswith("1 ")
