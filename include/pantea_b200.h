@@ -192,6 +192,12 @@ int pantea_md_run(pantea_workspace* ws, void* positions, void* velocities, void*
                   const int32_t* types, int64_t n_atoms, const double* box, int64_t n_steps,
                   const pantea_md_params* params, double* scalars, void* stream);
 
+/* -- Lennard-Jones potential on the bound neighbour rows: replaces `_jitted_compute_total_energy` and `_compute_forces`
+      (reference simulation/lennard_jones.py:73-123).  forces = +dE/dr_i, as the reference returns (sic).
+      e_atom [n] (half of each pair energy per atom) / forces [n,3] / e_total [1] may each be NULL. */
+int pantea_lj_energy_forces(pantea_workspace* ws, double sigma, double epsilon, void* e_atom, void* forces,
+                            void* e_total, void* stream);
+
 /* -- measurement helpers (bench.py) ------------------------------------------------------------ */
 /* number of kernel launches issued through this library since load */
 int64_t pantea_launch_count(void);

@@ -317,3 +317,16 @@ def models_from_specs(specs) -> List[ElementModel]:
         out.append(ElementModel(spec.atom_type, symfuncs_from_spec(spec), spec.scale_type, params, layers,
                                 spec.scale_min, spec.scale_max))
     return out
+
+
+# ----------------------------------------------------------------------------- Lennard-Jones (driver tests)
+def lj_energy_and_gradient(positions: Tensor, box: Optional[Tensor], sigma: float, epsilon: float,
+                           r_cutoff: float) -> Tuple[Tensor, Tensor]:
+    """Dense LJ energy and the reference's "forces" (= +dE/dr) -- pantea/simulation/lennard_jones.py:73-123."""
+    r, d = distances_with_aux(positions, positions, box)
+    mask = cutoff_mask(r, r_cutoff)
+    rs = torch.where(mask, r, torch.ones_like(r))
+    t6 = (sigma / rs) ** 6
+    e_pair = torch.where(mask, 4.0 * epsilon * t6 * (t6 - 1.0), torch.zeros_like(r))
+    coef = torch.where(mask, -24.0 * epsilon / (rs * rs) * t6 * (2.0 * t6 - 1.0), torch.zeros_like(r))
+    return 0.5 * e_pair.sum(), (coef[..., None] * d).sum(dim=1)

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "pantea_md_kinetic_energy": (C.c_int, [_VP, _VP, _I64, _I64, _VP, _I32, _VP]),
     "pantea_md_rescale_velocities": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _DBL, _DBL, _DBL, _DBL, _I32, _VP]),
     "pantea_md_run": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I64, C.POINTER(_DBL), _I64, C.POINTER(MDParams), _VP, _VP]),
+    "pantea_lj_energy_forces": (C.c_int, [_VP, _DBL, _DBL, _VP, _VP, _VP, _VP]),
     "pantea_launch_count": (_I64, []),
     "pantea_bench_fma": (C.c_int, [_I32, _I32, _I32, _I32, _VP, C.POINTER(_DBL), _VP]),
     "pantea_l2_flush": (C.c_int, [_VP, _I64, _VP]),
