@@ -325,6 +325,17 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
 #pragma unroll
     for (int m = 0; m < MCH; ++m) { aG[m] = 0; aX[m] = 0; aY[m] = 0; aZ[m] = 0; }
 
+    // software pipeline over the pair list (it lives in HBM/L2): the entries of the iterations after next are loaded
+    // while the current triplets are evaluated, so their latency is hidden behind ~2 x 185 instructions
+    constexpr int PF = 2;  // prefetch distance in iterations
+    int jk_q[PF][NU];
+#pragma unroll
+    for (int d = 0; d < PF; ++d)
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int e = d * S * NU + u * S + tid_atom;
+            jk_q[d][u] = count > 0 ? list[e < count ? e : 0] : 0;
+        }
     for (int base = 0; base < count; base += S * NU) {
         int jk[NU];
         bool valid[NU];
@@ -332,7 +343,11 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
         for (int u = 0; u < NU; ++u) {
             const int e = base + u * S + tid_atom;
             valid[u] = e < count;
-            jk[u] = list[valid[u] ? e : 0];
+            jk[u] = jk_q[0][u];
+#pragma unroll
+            for (int d = 0; d + 1 < PF; ++d) jk_q[d][u] = jk_q[d + 1][u];
+            const int en = e + PF * S * NU;
+            jk_q[PF - 1][u] = list[en < count ? en : 0];
         }
         T dxj[NU], dyj[NU], dzj[NU], rj[NU], ivj[NU], fcj[NU], dxk[NU], dyk[NU], dzk[NU], rk[NU], ivk[NU], fck[NU];
         T dfj[NU], dfk[NU], r2[NU], rjk2[NU];
