@@ -34,6 +34,10 @@ constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kAtomsPerBlock = 4;   // eval kernel, WPA == 1 configuration: 4 warps, one atom each
 constexpr int kFilterWarps = 8;     // pair filter: 8 warps per block, one atom each
 constexpr int kNU = PANTEA_TRIPLETS_PER_LANE;
+#ifndef PANTEA_STAGE_ITERS
+#define PANTEA_STAGE_ITERS 8
+#endif
+constexpr int kStageIters = PANTEA_STAGE_ITERS;  // pair-list iterations staged per cp.async group
 
 struct BoxArgK {
     double lx, ly, lz;
@@ -304,7 +308,7 @@ template <typename T, int WPA, bool GRAD, int MCH, bool FAST>
 __device__ __forceinline__ void angular_group(const ElementTable& tab, const AngularGroup& grp, int m0, int mc,
                                               const NbrBlock<T>& nb, const int32_t* __restrict__ list, int count,
                                               bool wrap_jk, T lx, T ly, T lz, int lane, int tid_atom, T* my_acc,
-                                              const T* __restrict__ etab, unsigned long long& cnt_trip) {
+                                              const T* __restrict__ etab, int* stage, unsigned long long& cnt_trip) {
     constexpr int NU = kNU;
     constexpr int S = 32 * WPA;
     const int ctype = tab.cls[grp.cls].type;
@@ -325,29 +329,41 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
 #pragma unroll
     for (int m = 0; m < MCH; ++m) { aG[m] = 0; aX[m] = 0; aY[m] = 0; aZ[m] = 0; }
 
-    // software pipeline over the pair list (it lives in HBM/L2): the entries of the iterations after next are loaded
-    // while the current triplets are evaluated, so their latency is hidden behind ~2 x 185 instructions
-    constexpr int PF = 2;  // prefetch distance in iterations
-    int jk_q[PF][NU];
+    // software pipeline over the pair list (it lives in HBM/L2): every lane copies its own entries of the next
+    // kStageIters iterations into a shared-memory ring with cp.async while the current chunk is evaluated. The copies
+    // are tracked by cp.async groups, not by the register scoreboard, so a consumer never waits on a younger load.
+    constexpr int CH = kStageIters;
+    const int n_iter = (count + S * NU - 1) / (S * NU);
+    auto stage_chunk = [&](int chunk) {
+        int* dst = stage + (chunk & 1) * (CH * NU * 32) + lane;
 #pragma unroll
-    for (int d = 0; d < PF; ++d)
+        for (int i = 0; i < CH; ++i)
 #pragma unroll
-        for (int u = 0; u < NU; ++u) {
-            const int e = d * S * NU + u * S + tid_atom;
-            jk_q[d][u] = count > 0 ? list[e < count ? e : 0] : 0;
+            for (int u = 0; u < NU; ++u) {
+                const int e = ((chunk * CH + i) * NU + u) * S + tid_atom;
+                if (e < count) cp_async4(dst + (i * NU + u) * 32, list + e);
+            }
+        cp_async_commit();
+    };
+    if (n_iter > 0) stage_chunk(0);
+    for (int it = 0; it < n_iter; ++it) {
+        const int base = it * S * NU;
+        if (it % CH == 0) {
+            if (it + CH < n_iter) {
+                stage_chunk(it / CH + 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
         }
-    for (int base = 0; base < count; base += S * NU) {
+        const int* src = stage + ((it / CH) & 1) * (CH * NU * 32) + (it % CH) * NU * 32 + lane;
         int jk[NU];
         bool valid[NU];
 #pragma unroll
         for (int u = 0; u < NU; ++u) {
             const int e = base + u * S + tid_atom;
             valid[u] = e < count;
-            jk[u] = jk_q[0][u];
-#pragma unroll
-            for (int d = 0; d + 1 < PF; ++d) jk_q[d][u] = jk_q[d + 1][u];
-            const int en = e + PF * S * NU;
-            jk_q[PF - 1][u] = list[en < count ? en : 0];
+            jk[u] = valid[u] ? src[u * 32] : 0;
         }
         T dxj[NU], dyj[NU], dzj[NU], rj[NU], ivj[NU], fcj[NU], dxk[NU], dyk[NU], dzk[NU], rk[NU], ivk[NU], fck[NU];
         T dfj[NU], dfk[NU], r2[NU], rjk2[NU];
@@ -454,6 +470,7 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
     constexpr int S = 32 * WPA;                     // threads per atom
     __shared__ T s_etab[64];                        // 2^(i/64) for the table-driven exponential
     exp2_table_fill(s_etab, threadIdx.x, blockDim.x);
+    __shared__ int s_stage[4][2 * kStageIters * kNU * 32];  // per-warp pair-list staging ring (128 threads per block)
     __syncthreads();
     const int w = blockIdx.x * (WPA == 1 ? kAtomsPerBlock : 1) + atom_in_block;
     if (w >= a.n_work) return;
@@ -560,10 +577,10 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
                 const int mc = grp.count - m0 < MCH ? grp.count - m0 : MCH;
                 if (fast)
                     angular_group<T, WPA, GRAD, MCH, true>(tab, grp, m0, mc, nb, lists + lo, count, wrap_jk, lx, ly, lz, lane,
-                                                           tid_atom, my_acc, s_etab, cnt_trip);
+                                                           tid_atom, my_acc, s_etab, s_stage[threadIdx.x >> 5], cnt_trip);
                 else
                     angular_group<T, WPA, GRAD, MCH, false>(tab, grp, m0, mc, nb, lists + lo, count, wrap_jk, lx, ly, lz, lane,
-                                                            tid_atom, my_acc, s_etab, cnt_trip);
+                                                            tid_atom, my_acc, s_etab, s_stage[threadIdx.x >> 5], cnt_trip);
             }
         }
     }
