@@ -334,115 +334,109 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
     // are tracked by cp.async groups, not by the register scoreboard, so a consumer never waits on a younger load.
     constexpr int CH = kStageIters;
     const int n_iter = (count + S * NU - 1) / (S * NU);
-    auto stage_chunk = [&](int chunk) {
+    const int n_chunks = (n_iter + CH - 1) / CH;
+    const bool counting = cnt_trip != ~0ull;
+    auto stage_chunk = [&](int chunk) {  // entries past the end re-read entry 0: every lane always holds a real pair
         int* dst = stage + (chunk & 1) * (CH * NU * 32) + lane;
+        int e = chunk * (CH * NU * S) + tid_atom;
 #pragma unroll
-        for (int i = 0; i < CH; ++i)
-#pragma unroll
-            for (int u = 0; u < NU; ++u) {
-                const int e = ((chunk * CH + i) * NU + u) * S + tid_atom;
-                if (e < count) cp_async4(dst + (i * NU + u) * 32, list + e);
-            }
+        for (int i = 0; i < CH * NU; ++i, e += S) cp_async4(dst + i * 32, list + (e < count ? e : 0));
         cp_async_commit();
     };
-    if (n_iter > 0) stage_chunk(0);
-    for (int it = 0; it < n_iter; ++it) {
-        const int base = it * S * NU;
-        if (it % CH == 0) {
-            if (it + CH < n_iter) {
-                stage_chunk(it / CH + 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-        }
-        const int* src = stage + ((it / CH) & 1) * (CH * NU * 32) + (it % CH) * NU * 32 + lane;
-        int jk[NU];
-        bool valid[NU];
-#pragma unroll
-        for (int u = 0; u < NU; ++u) {
-            const int e = base + u * S + tid_atom;
-            valid[u] = e < count;
-            jk[u] = valid[u] ? src[u * 32] : 0;
-        }
-        T dxj[NU], dyj[NU], dzj[NU], rj[NU], ivj[NU], fcj[NU], dxk[NU], dyk[NU], dzk[NU], rk[NU], ivk[NU], fck[NU];
-        T dfj[NU], dfk[NU], r2[NU], rjk2[NU];
-#pragma unroll
-        for (int u = 0; u < NU; ++u) {
-            const int j = jk[u] & 0xffff, k = jk[u] >> 16;
-            const T* pj = nb.rec + j * nb.stride;
-            const T* pk = nb.rec + k * nb.stride;
-            dxj[u] = pj[0]; dyj[u] = pj[1]; dzj[u] = pj[2]; rj[u] = pj[3]; ivj[u] = pj[4]; fcj[u] = pj[nb.fco];
-            dxk[u] = pk[0]; dyk[u] = pk[1]; dzk[u] = pk[2]; rk[u] = pk[3]; ivk[u] = pk[4]; fck[u] = pk[nb.fco];
-            dfj[u] = GRAD ? pj[nb.fco + 1] : (T)0; dfk[u] = GRAD ? pk[nb.fco + 1] : (T)0;
-        }
-#pragma unroll
-        for (int u = 0; u < NU; ++u) {  // r_jk = |pbc(d_ij - d_ik)| (reference acsf.py:316-320), exact
-            T ex = dxj[u] - dxk[u], ey = dyj[u] - dyk[u], ez = dzj[u] - dzk[u];
-            if (wrap_jk) { ex = min_image(ex, lx); ey = min_image(ey, ly); ez = min_image(ez, lz); }
-            rjk2[u] = ex * ex + ey * ey + ez * ez;
-            valid[u] = valid[u] && rjk2[u] > (T)0;  // k == j / coincident atoms excluded (acsf.py:325)
-            r2[u] = rj[u] * rj[u] + rk[u] * rk[u];
-        }
-        T fcjk[NU];
-        if (FAST) {
-            T rjk[NU], t[NU];
-#pragma unroll
-            for (int u = 0; u < NU; ++u) rjk[u] = fast_sqrt(valid[u] ? rjk2[u] : (T)1);
-#pragma unroll
-            for (int u = 0; u < NU; ++u) t[u] = fast_tanh_pos_tab<T>((T)1 - rjk[u] * inv_rc, etab);
-#pragma unroll
-            for (int u = 0; u < NU; ++u) {
-                fcjk[u] = (valid[u] && rjk[u] < rc) ? t[u] * t[u] * t[u] : (T)0;
-                r2[u] += rjk2[u];
-            }
+    if (n_chunks > 0) stage_chunk(0);
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        if (chunk + 1 < n_chunks) {
+            stage_chunk(chunk + 1);
+            cp_async_wait<1>();
         } else {
+            cp_async_wait<0>();
+        }
+        const int* src = stage + (chunk & 1) * (CH * NU * 32) + lane;
+        int e0 = chunk * (CH * NU * S) + tid_atom;
+        const int n_in = min(CH, n_iter - chunk * CH);
+        for (int i = 0; i < n_in; ++i, src += NU * 32, e0 += NU * S) {
+            bool valid[NU];
+            // neighbour records: [u_x, u_y, u_z, r, 1/r, (fc, fc'/fc) per cutoff class], u = d / r
+            T uxj[NU], uyj[NU], uzj[NU], rj[NU], ivj[NU], fcj[NU], uxk[NU], uyk[NU], uzk[NU], rk[NU], ivk[NU], fck[NU];
+            T qj[NU], qk[NU], r2[NU], rjk2[NU];
 #pragma unroll
             for (int u = 0; u < NU; ++u) {
-                fcjk[u] = (T)1;
-                if (is_g3) { fcjk[u] = cutoff_value_sq<T>(ctype, valid[u] ? rjk2[u] : (T)1, rc, inv_rc); r2[u] += rjk2[u]; }
-                if (!valid[u]) fcjk[u] = (T)0;
+                const int jk = src[u * 32];
+                valid[u] = e0 + u * S < count;
+                const T* pj = nb.rec + (jk & 0xffff) * nb.stride;
+                const T* pk = nb.rec + (jk >> 16) * nb.stride;
+                uxj[u] = pj[0]; uyj[u] = pj[1]; uzj[u] = pj[2]; rj[u] = pj[3]; ivj[u] = pj[4]; fcj[u] = pj[nb.fco];
+                uxk[u] = pk[0]; uyk[u] = pk[1]; uzk[u] = pk[2]; rk[u] = pk[3]; ivk[u] = pk[4]; fck[u] = pk[nb.fco];
+                qj[u] = GRAD ? pj[nb.fco + 1] : (T)0; qk[u] = GRAD ? pk[nb.fco + 1] : (T)0;
             }
-        }
-        T ivjk[NU], cost[NU], fprod[NU], dfp_j[NU], dfp_k[NU], cj[NU], ck[NU];
 #pragma unroll
-        for (int u = 0; u < NU; ++u) {
-            ivjk[u] = ivj[u] * ivk[u];
-            cost[u] = (dxj[u] * dxk[u] + dyj[u] * dyk[u] + dzj[u] * dzk[u]) * ivjk[u];
-            fprod[u] = fcj[u] * fck[u] * fcjk[u];
-            if (GRAD) {
-                dfp_j[u] = dfj[u] * fck[u] * fcjk[u]; dfp_k[u] = fcj[u] * dfk[u] * fcjk[u];
-                cj[u] = ivjk[u] - cost[u] * ivj[u] * ivj[u]; ck[u] = ivjk[u] - cost[u] * ivk[u] * ivk[u];
+            for (int u = 0; u < NU; ++u) {  // r_jk = |pbc(d_ij - d_ik)| (reference acsf.py:316-320)
+                T ex = uxj[u] * rj[u] - uxk[u] * rk[u], ey = uyj[u] * rj[u] - uyk[u] * rk[u], ez = uzj[u] * rj[u] - uzk[u] * rk[u];
+                if (wrap_jk) { ex = min_image(ex, lx); ey = min_image(ey, ly); ez = min_image(ez, lz); }
+                rjk2[u] = ex * ex + ey * ey + ez * ez;
+                r2[u] = rj[u] * rj[u] + rk[u] * rk[u];
             }
-        }
+            T fcjk[NU];
+            if (FAST) {
+                // coincident neighbours (r_jk == 0, excluded by acsf.py:325) give rsqrt(0) -> NaN in rjk and t; the
+                // comparison below is then false and the select discards them
+                T rjk[NU], t[NU];
 #pragma unroll
-        for (int m = 0; m < MCH; ++m) {
-            if (MCH == 1 || m < mc) {
-                T e[NU];
+                for (int u = 0; u < NU; ++u) rjk[u] = fast_sqrt_loop(rjk2[u]);
 #pragma unroll
-                for (int u = 0; u < NU; ++u) e[u] = fast_exp_tab<true>(m_neta[m] * r2[u], etab);
+                for (int u = 0; u < NU; ++u) t[u] = fast_tanh_pos_tab<T>((T)1 - rjk[u] * inv_rc, etab);
 #pragma unroll
                 for (int u = 0; u < NU; ++u) {
-                    const T bs = (T)1 + m_lam[m] * cost[u];
-                    T pw1 = (T)1;
-                    if (!FAST && m_iz[m] != 1) pw1 = m_iz[m] > 1 ? powi<T>(bs, m_iz[m] - 1) : pow_general<T>(bs, m_zm1[m]);
-                    const T ang_e = m_pref[m] * pw1 * bs * e[u];
-                    aG[m] += ang_e * fprod[u];
-                    if (GRAD) {
-                        const T Tc = m_zl[m] * pw1 * e[u] * fprod[u];
-                        const T Tij = ang_e * (dfp_j[u] + m_2neta[m] * rj[u] * fprod[u]);
-                        const T Tik = ang_e * (dfp_k[u] + m_2neta[m] * rk[u] * fprod[u]);
-                        const T Aj = Tc * cj[u] + Tij * ivj[u], Ak = Tc * ck[u] + Tik * ivk[u];
-                        aX[m] += Aj * dxj[u] + Ak * dxk[u];
-                        aY[m] += Aj * dyj[u] + Ak * dyk[u];
-                        aZ[m] += Aj * dzj[u] + Ak * dzk[u];
+                    fcjk[u] = (valid[u] && rjk[u] < rc) ? t[u] * t[u] * t[u] : (T)0;
+                    r2[u] += rjk2[u];
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    valid[u] = valid[u] && rjk2[u] > (T)0;  // k == j / coincident atoms excluded (acsf.py:325)
+                    fcjk[u] = (T)1;
+                    if (is_g3) { fcjk[u] = cutoff_value_sq<T>(ctype, valid[u] ? rjk2[u] : (T)1, rc, inv_rc); r2[u] += rjk2[u]; }
+                    if (!valid[u]) fcjk[u] = (T)0;
+                }
+            }
+            // with P = fc_j fc_k fc_jk, A = pref (1 + lambda cos)^zeta exp(-eta r2):   G += A P  and
+            //   dG/dr_i -= sum over j of [A P (q_j - 2 eta r_j) + T_c (1/r_k - cos / r_j)] u_j,   q = fc'/fc,
+            //   T_c = pref zeta lambda (1 + lambda cos)^(zeta-1) exp(-eta r2) P     (sign folded into the caller)
+            T cost[NU], fprod[NU];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                cost[u] = uxj[u] * uxk[u] + uyj[u] * uyk[u] + uzj[u] * uzk[u];
+                fprod[u] = fcj[u] * fck[u] * fcjk[u];
+            }
+#pragma unroll
+            for (int m = 0; m < MCH; ++m) {
+                if (MCH == 1 || m < mc) {
+                    T e[NU];
+#pragma unroll
+                    for (int u = 0; u < NU; ++u) e[u] = fast_exp_tab<true>(m_neta[m] * r2[u], etab);
+#pragma unroll
+                    for (int u = 0; u < NU; ++u) {
+                        const T bs = (T)1 + m_lam[m] * cost[u];
+                        T pw1 = (T)1;
+                        if (!FAST && m_iz[m] != 1) pw1 = m_iz[m] > 1 ? powi<T>(bs, m_iz[m] - 1) : pow_general<T>(bs, m_zm1[m]);
+                        const T ep = e[u] * fprod[u] * pw1;
+                        const T ap = m_pref[m] * bs * ep;  // this triplet's contribution to G
+                        aG[m] += ap;
+                        if (GRAD) {
+                            const T Tc = m_zl[m] * ep;
+                            const T Bj = Tc * (ivk[u] - cost[u] * ivj[u]) + ap * (qj[u] + m_2neta[m] * rj[u]);
+                            const T Bk = Tc * (ivj[u] - cost[u] * ivk[u]) + ap * (qk[u] + m_2neta[m] * rk[u]);
+                            aX[m] += Bj * uxj[u] + Bk * uxk[u];
+                            aY[m] += Bj * uyj[u] + Bk * uyk[u];
+                            aZ[m] += Bj * uzj[u] + Bk * uzk[u];
+                        }
                     }
                 }
             }
-        }
-        if (cnt_trip != ~0ull) {
+            if (counting) {
 #pragma unroll
-            for (int u = 0; u < NU; ++u) cnt_trip += (valid[u] && fcjk[u] != (T)0) ? (unsigned long long)mc : 0ull;
+                for (int u = 0; u < NU; ++u) cnt_trip += (valid[u] && fcjk[u] != (T)0) ? (unsigned long long)mc : 0ull;
+            }
         }
     }
 
@@ -516,7 +510,8 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
                 if (pbc) { dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz); }
                 const T r = norm3_rn(dx, dy, dz);
                 T* p = snb + (size_t)n * stride;
-                p[0] = dx; p[1] = dy; p[2] = dz; p[3] = r; p[4] = (T)1 / r;
+                const T iv = (T)1 / r;
+                p[0] = dx * iv; p[1] = dy * iv; p[2] = dz * iv; p[3] = r; p[4] = iv;
                 for (int c = 0; c < n_cls; ++c) {
                     T fc, dfc;
                     const int ct = tab.cls[c].type;
@@ -528,7 +523,7 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
                     } else {
                         cutoff_eval_ool<T>(ct, r, rcc, &fc, &dfc);
                     }
-                    p[5 + 2 * c] = fc; p[6 + 2 * c] = dfc;
+                    p[5 + 2 * c] = fc; p[6 + 2 * c] = fc != (T)0 ? dfc / fc : (T)0;  // logarithmic derivative
                 }
             }
         }
@@ -547,16 +542,16 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
         T g = 0, gx = 0, gy = 0, gz = 0;
         for (int n = lo + tid_atom; n < hi; n += S) {
             const T* p = snb + (size_t)n * stride;
-            const T r = p[3], fc = p[fco], dfc = p[fco + 1];
+            const T r = p[3], fc = p[fco], q = p[fco + 1];
             T val, dval;
-            if (sf.kind == PANTEA_G1) { val = fc; dval = dfc; }
+            if (sf.kind == PANTEA_G1) { val = fc; dval = fc * q; }
             else {
                 const T dr = r - rs, ex = fast_exp(-eta * dr * dr);
-                val = ex * fc; dval = ex * (dfc - (T)2 * eta * dr * fc);
+                val = ex * fc; dval = val * (q - (T)2 * eta * dr);
             }
             g += val;
             ++cnt_rad;
-            if (GRAD) { const T sc = dval * p[4]; gx += sc * p[0]; gy += sc * p[1]; gz += sc * p[2]; }
+            if (GRAD) { gx += dval * p[0]; gy += dval * p[1]; gz += dval * p[2]; }
         }
         g = warp_sum(g);
         if (GRAD) { gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz); }

@@ -113,6 +113,18 @@ __device__ __forceinline__ double fast_sqrt(double a) {  // sqrt(a) for normal p
     return fma(0.5 * y, fma(-s, s, a), s);   // one correction step on the root itself
 }
 __device__ __forceinline__ float fast_sqrt(float a) { return __fsqrt_rn(a); }
+// triplet-loop variant: two Newton steps on the reciprocal root already reach ~2 ulp, the final correction is dropped;
+// a == 0 yields NaN (the caller's comparison then rejects the lane)
+__device__ __forceinline__ double fast_sqrt_loop(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-a * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    return a * y;
+}
+__device__ __forceinline__ float fast_sqrt_loop(float a) { return __fsqrt_rn(a); }
 
 // Taylor coefficients 1/n!, n = 0..12, in constant memory so that they fold into the FMA operands
 static __constant__ double kExpC[13] = {
@@ -143,7 +155,7 @@ __device__ __forceinline__ double fast_exp_t(double y) {
 }
 // Table-driven exp for the triplet loop: exp(y) = 2^k * T[i] * p(f) with n = round(y * 64/ln2) = 64 k + i,
 // f = y - n ln2/64 (|f| <= ln2/128) and a degree-5 polynomial; T[i] = 2^(i/64) lives in shared memory
-// (`exp2_table_fill`).  ~10 FP64 instructions instead of ~18; arguments below -700 are clamped.
+// (`exp2_table_fill`).  ~10 FP64 instructions instead of ~18; CLAMP: arguments below -700 return 0.
 static __constant__ double kExpT[6] = {92.332482616893657 /* 64/ln2 */, 6755399441055744.0 /* 1.5 * 2^52 */,
                                        -6.93147180369123816490e-01 / 64.0, -1.90821492927058770002e-10 / 64.0,
                                        1.66666666666666666667e-01, 4.16666666666666666667e-02};
@@ -153,11 +165,10 @@ __device__ __forceinline__ void exp2_table_fill(double* tab, int tid, int nthrea
 __device__ __forceinline__ void exp2_table_fill(float*, int, int) {}
 template <bool CLAMP>
 __device__ __forceinline__ double fast_exp_tab(double y, const double* __restrict__ tab) {
-    const double yc = CLAMP ? fmax(y, -700.0) : y;
-    const double t = fma(yc, kExpT[0], kExpT[1]);
+    const double t = fma(y, kExpT[0], kExpT[1]);
     const int n = __double2loint(t);
     const double nf = t - kExpT[1];
-    double f = fma(nf, kExpT[2], yc);
+    double f = fma(nf, kExpT[2], y);
     f = fma(nf, kExpT[3], f);
     double p = fma(8.33333333333333333333e-03, f, kExpT[5]);
     p = fma(p, f, kExpT[4]);
@@ -165,7 +176,10 @@ __device__ __forceinline__ double fast_exp_tab(double y, const double* __restric
     p = fma(p, f, 1.0);
     p = fma(p, f, 1.0);
     p *= tab[n & 63];
-    return __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
+    const int hi = __double2hiint(p) + ((n >> 6) << 20), lo = __double2loint(p);
+    // y < -700 (sign bit set, magnitude bits above those of 700.0): the result underflows, return 0 (integer test)
+    const bool under = CLAMP && (unsigned)__double2hiint(y) > 0xC085E000u;
+    return __hiloint2double(under ? 0 : hi, under ? 0 : lo);
 }
 template <bool CLAMP>
 __device__ __forceinline__ float fast_exp_tab(float y, const float*) { return expf(y); }
