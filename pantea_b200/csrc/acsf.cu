@@ -508,22 +508,28 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
                 const int n = u == 0 ? n0 : n1;
                 T dx = sub_rn(ri.x, rj.x), dy = sub_rn(ri.y, rj.y), dz = sub_rn(ri.z, rj.z);
                 if (pbc) { dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz); }
-                const T r = norm3_rn(dx, dy, dz);
+                // r and 1/r from one reciprocal-root seed (the exact-rounding rule only matters for the neighbour
+                // predicate, which neighbor_rows_kernel has already applied)
+                const T r2n = dx * dx + dy * dy + dz * dz;
+                const T iv = fast_rsqrt(r2n), r = r2n * iv;
                 T* p = snb + (size_t)n * stride;
-                const T iv = (T)1 / r;
                 p[0] = dx * iv; p[1] = dy * iv; p[2] = dz * iv; p[3] = r; p[4] = iv;
                 for (int c = 0; c < n_cls; ++c) {
-                    T fc, dfc;
+                    T fc, q;  // cutoff value and its logarithmic derivative fc'/fc
                     const int ct = tab.cls[c].type;
                     const T rcc = (T)tab.cls[c].rc;
                     if (ct == PANTEA_CUT_TANHU) {  // inline fast path for the common cutoff
-                        const T t = fast_tanh_pos<T>((T)1 - r / rcc), t2 = t * t;
-                        const bool in = r < rcc;
-                        fc = in ? t2 * t : (T)0; dfc = in ? ((T)-3 / rcc) * t2 * ((T)1 - t2) : (T)0;
+                        const T irc = fast_rcp(rcc);
+                        const T t = fast_tanh_pos<T>((T)1 - r * irc);
+                        const bool in = r < rcc && t > (T)0;
+                        fc = in ? t * t * t : (T)0;
+                        q = in ? (T)-3 * irc * ((T)1 - t * t) * fast_rcp(t) : (T)0;
                     } else {
+                        T dfc;
                         cutoff_eval_ool<T>(ct, r, rcc, &fc, &dfc);
+                        q = fc != (T)0 ? dfc / fc : (T)0;
                     }
-                    p[5 + 2 * c] = fc; p[6 + 2 * c] = fc != (T)0 ? dfc / fc : (T)0;  // logarithmic derivative
+                    p[5 + 2 * c] = fc; p[6 + 2 * c] = q;
                 }
             }
         }

@@ -113,6 +113,16 @@ __device__ __forceinline__ double fast_sqrt(double a) {  // sqrt(a) for normal p
     return fma(0.5 * y, fma(-s, s, a), s);   // one correction step on the root itself
 }
 __device__ __forceinline__ float fast_sqrt(float a) { return __fsqrt_rn(a); }
+// 1/sqrt(a) for normal positive a, ~2 ulp
+__device__ __forceinline__ double fast_rsqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-a * y, y, 1.0);
+    return fma(0.5 * y, e, y);
+}
+__device__ __forceinline__ float fast_rsqrt(float a) { return 1.0f / __fsqrt_rn(a); }
 // triplet-loop variant: two Newton steps on the reciprocal root already reach ~2 ulp, the final correction is dropped;
 // a == 0 yields NaN (the caller's comparison then rejects the lane)
 __device__ __forceinline__ double fast_sqrt_loop(double a) {
