@@ -189,9 +189,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const At
         return;
     }
     const ElementTable& tab = a.tables[etype];
-    const int item_cap = a.scap * ((a.scap + 31) / 32);  // worst case: every neighbour pairs with every neighbour
     float4* sf4 = (float4*)smem_raw + (size_t)wib * a.scap;
-    int* items = (int*)(smem_raw + (size_t)kFilterWarps * a.scap * sizeof(float4)) + (size_t)wib * item_cap;
 
     Segments sg;
     sg.load(a.tcount + (size_t)slot * kBuckets, a.scap);
@@ -225,6 +223,8 @@ __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const At
     __syncwarp();
 
     int32_t* list = a.pairs + (size_t)w * a.pair_cap;
+    int pair_cap = a.pair_cap;
+    asm volatile("" : "+l"(list), "+r"(pair_cap));  // keep both in registers: the store below is one IMAD.WIDE + STG
     const unsigned lt_mask = (1u << lane) - 1u;
     int off = 0;  // running number of pairs (may exceed pair_cap: then only counted)
     for (int gi = 0; gi < tab.n_groups; ++gi) {
@@ -237,51 +237,36 @@ __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const At
         const float rc2f = grp.kind == PANTEA_G3 ? rcf * rcf * 1.0001f + 1e-4f : 3.0e38f;
         const int cls_bit = 1 << grp.cls;
         const int kbase = same ? bj : bk;
-        // work items = (neighbour j, 32-wide chunk of partners k), enumerated j-major so that the pair order is
-        // deterministic; building the item list first lets every iteration below process two full items even when a
-        // neighbour has only a few partners left (triangular same-type loops)
-        int n_items = 0;
-        for (int j0 = 0; j0 < nj; j0 += 32) {
-            const int aj = j0 + lane;
-            const int start = same ? aj + 1 : 0;
-            int cnt = 0;
-            if (aj < nj && (__float_as_int(sf4[bj + aj].w) & cls_bit) && nk > start) cnt = (nk - start + 31) >> 5;
-            int incl = cnt;
+        // every lane keeps one partner k in registers while the warp sweeps over the neighbours j (broadcast reads);
+        // same-type groups take the unordered pairs j < k, so the sweep stops at the chunk's last partner.  The pair
+        // order (k chunk, j, k) is fixed, hence the evaluation's summation order is deterministic.
+        for (int k0 = 0; k0 < nk; k0 += 32) {
+            const int kk = k0 + lane;
+            const float4 fk = sf4[kbase + (kk < nk ? kk : 0)];
+            const bool k_ok = kk < nk && (__float_as_int(fk.w) & cls_bit);
+            const int k_hi = (kbase + kk) << 16;
+            const int j_end = same ? min(nj, k0 + 31) : nj;
+            for (int aj = 0; aj < j_end; aj += 2) {
+                const bool has1 = aj + 1 < j_end;
+                const float4 fj[2] = {sf4[bj + aj], sf4[bj + (has1 ? aj + 1 : aj)]};
+                bool live[2];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(kFullMask, incl, o);
-                if (lane >= o) incl += y;
-            }
-            const int base_i = n_items + incl - cnt;
-            for (int c = 0; c < cnt; ++c) items[base_i + c] = (bj + aj) | ((start + 32 * c) << 16);
-            n_items += __shfl_sync(kFullMask, incl, 31);
-        }
-        __syncwarp();
-        for (int it = 0; it < n_items; it += 2) {
-            const bool has1 = it + 1 < n_items;
-            const int item[2] = {items[it], items[has1 ? it + 1 : it]};
-            bool live[2];
-            int jk[2];
+                for (int c = 0; c < 2; ++c) {
+                    float ex = fj[c].x - fk.x, ey = fj[c].y - fk.y, ez = fj[c].z - fk.z;
+                    if (wrap_jk) { ex = min_image(ex, flx); ey = min_image(ey, fly); ez = min_image(ez, flz); }
+                    const float d2 = ex * ex + ey * ey + ez * ez;
+                    live[c] = k_ok && d2 < rc2f && (__float_as_int(fj[c].w) & cls_bit) && (!same || aj + c < kk) &&
+                              (c == 0 || has1);
+                }
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int j = item[c] & 0xffff, kk = (item[c] >> 16) + lane;
-                const float4 fj = sf4[j];
-                const float4 fk = sf4[kbase + (kk < nk ? kk : 0)];
-                float ex = fj.x - fk.x, ey = fj.y - fk.y, ez = fj.z - fk.z;
-                if (wrap_jk) { ex = min_image(ex, flx); ey = min_image(ey, fly); ez = min_image(ez, flz); }
-                const float d2 = ex * ex + ey * ey + ez * ez;
-                live[c] = kk < nk && d2 < rc2f && (__float_as_int(fk.w) & cls_bit) && (c == 0 || has1);
-                jk[c] = j | ((kbase + kk) << 16);
-            }
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const unsigned mask = __ballot_sync(kFullMask, live[c]);
-                const int pos = off + __popc(mask & lt_mask);
-                if (live[c] && pos < a.pair_cap) list[pos] = jk[c];
-                off += __popc(mask);
+                for (int c = 0; c < 2; ++c) {
+                    const unsigned mask = __ballot_sync(kFullMask, live[c]);
+                    const int pos = off + __popc(mask & lt_mask);
+                    if (live[c] && pos < pair_cap) list[pos] = (bj + aj + c) | k_hi;
+                    off += __popc(mask);
+                }
             }
         }
-        __syncwarp();
     }
     if (lane == 0) {
         off_out[tab.n_groups] = off < a.pair_cap ? off : a.pair_cap;
@@ -770,7 +755,7 @@ static int launch_mch(const AtomArgs<T>& a, int max_members, cudaStream_t st) {
 
 template <typename T>
 static int launch_filter(const AtomArgs<T>& a, cudaStream_t st) {
-    const size_t smem = (size_t)kFilterWarps * a.scap * (sizeof(float4) + sizeof(int) * ((a.scap + 31) / 32));
+    const size_t smem = (size_t)kFilterWarps * a.scap * sizeof(float4);
     auto kern = pair_filter_kernel<T>;
     static size_t configured = 0;
     if (smem > configured) {
