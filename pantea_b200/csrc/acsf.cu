@@ -175,6 +175,44 @@ struct Segments {
 // ------------------------------------------------------------------------------------------------
 // 1. pair pre-filter
 // ------------------------------------------------------------------------------------------------
+// One sweep of the pair filter: neighbours j in [j_lo, j_hi) of the bucket starting at `js` against the lane's partner.
+// ORDER: also require j < k (the chunk's own neighbours in a same-type group); CLS: test j's cutoff-class bit (only
+// groups whose cutoff is shorter than the list radius); WRAP: minimum image on r_jk.  Two neighbours per iteration;
+// the staging array has one spare entry so that the odd tail can be read unconditionally.
+struct FilterSweep {
+    int32_t* list;
+    int pair_cap, cls_bit, k_hi, kk;
+    unsigned lt_mask;
+    float rc2f, flx, fly, flz;
+    float4 fk;
+    bool k_ok;
+    template <bool ORDER, bool CLS, bool WRAP>
+    __device__ __forceinline__ int run(const float4* __restrict__ sf4, int js, int j_lo, int j_hi, int off) const {
+        for (int aj = j_lo; aj < j_hi; aj += 2) {
+            const float4 fj[2] = {sf4[js + aj], sf4[js + aj + 1]};
+            bool live[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float ex = fj[c].x - fk.x, ey = fj[c].y - fk.y, ez = fj[c].z - fk.z;
+                if (WRAP) { ex = min_image(ex, flx); ey = min_image(ey, fly); ez = min_image(ez, flz); }
+                const float d2 = ex * ex + ey * ey + ez * ez;
+                live[c] = k_ok && d2 < rc2f;
+                if (CLS) live[c] = live[c] && (__float_as_int(fj[c].w) & cls_bit);
+                if (ORDER) live[c] = live[c] && aj + c < kk;
+            }
+            live[1] = live[1] && aj + 1 < j_hi;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const unsigned mask = __ballot_sync(kFullMask, live[c]);
+                const int pos = off + __popc(mask & lt_mask);
+                if (live[c] && pos < pair_cap) list[pos] = (js + aj + c) | k_hi;
+                off += __popc(mask);
+            }
+        }
+        return off;
+    }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const AtomArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -189,7 +227,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const At
         return;
     }
     const ElementTable& tab = a.tables[etype];
-    float4* sf4 = (float4*)smem_raw + (size_t)wib * a.scap;
+    float4* sf4 = (float4*)smem_raw + (size_t)wib * (a.scap + 1);  // + 1: see FilterSweep
 
     Segments sg;
     sg.load(a.tcount + (size_t)slot * kBuckets, a.scap);
@@ -235,36 +273,29 @@ __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const At
         const bool same = grp.type_j == grp.type_k;
         const float rcf = (float)tab.cls[grp.cls].rc;
         const float rc2f = grp.kind == PANTEA_G3 ? rcf * rcf * 1.0001f + 1e-4f : 3.0e38f;
-        const int cls_bit = 1 << grp.cls;
-        const int kbase = same ? bj : bk;
-        // every lane keeps one partner k in registers while the warp sweeps over the neighbours j (broadcast reads);
-        // same-type groups take the unordered pairs j < k, so the sweep stops at the chunk's last partner.  The pair
-        // order (k chunk, j, k) is fixed, hence the evaluation's summation order is deterministic.
-        for (int k0 = 0; k0 < nk; k0 += 32) {
+        // every lane keeps one partner k in registers while the warp sweeps over the neighbours j (broadcast reads).
+        // Same-type groups take the unordered pairs j < k: neighbours before the chunk pair with all of its lanes, the
+        // chunk's own neighbours need the order test.  Mixed groups sweep the bucket that leaves fewer idle lanes.
+        // The pair order (k chunk, j, k) is fixed, hence the evaluation's summation order is deterministic.
+        FilterSweep sw;
+        sw.list = list; sw.pair_cap = pair_cap; sw.lt_mask = lt_mask; sw.rc2f = rc2f; sw.cls_bit = 1 << grp.cls;
+        sw.flx = flx; sw.fly = fly; sw.flz = flz;
+        const bool swap = !same && nj * ((nk + 31) >> 5) > nk * ((nj + 31) >> 5);
+        const int js = swap ? bk : bj, njs = swap ? nk : nj;  // swept bucket
+        const int ks = swap ? bj : bk, nks = swap ? nj : nk;  // lane-resident bucket
+        const int variant = (tab.cls[grp.cls].rc < a.rc_list ? 1 : 0) | (wrap_jk ? 2 : 0);
+        for (int k0 = 0; k0 < nks; k0 += 32) {
             const int kk = k0 + lane;
-            const float4 fk = sf4[kbase + (kk < nk ? kk : 0)];
-            const bool k_ok = kk < nk && (__float_as_int(fk.w) & cls_bit);
-            const int k_hi = (kbase + kk) << 16;
-            const int j_end = same ? min(nj, k0 + 31) : nj;
-            for (int aj = 0; aj < j_end; aj += 2) {
-                const bool has1 = aj + 1 < j_end;
-                const float4 fj[2] = {sf4[bj + aj], sf4[bj + (has1 ? aj + 1 : aj)]};
-                bool live[2];
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    float ex = fj[c].x - fk.x, ey = fj[c].y - fk.y, ez = fj[c].z - fk.z;
-                    if (wrap_jk) { ex = min_image(ex, flx); ey = min_image(ey, fly); ez = min_image(ez, flz); }
-                    const float d2 = ex * ex + ey * ey + ez * ez;
-                    live[c] = k_ok && d2 < rc2f && (__float_as_int(fj[c].w) & cls_bit) && (!same || aj + c < kk) &&
-                              (c == 0 || has1);
-                }
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const unsigned mask = __ballot_sync(kFullMask, live[c]);
-                    const int pos = off + __popc(mask & lt_mask);
-                    if (live[c] && pos < pair_cap) list[pos] = (bj + aj + c) | k_hi;
-                    off += __popc(mask);
-                }
+            sw.fk = sf4[ks + (kk < nks ? kk : 0)];
+            sw.k_ok = kk < nks && (__float_as_int(sw.fk.w) & sw.cls_bit);
+            sw.k_hi = (ks + kk) << 16;
+            sw.kk = kk;
+            const int j_full = same ? min(njs, k0) : njs, j_diag = same ? min(njs, k0 + 31) : njs;
+            switch (variant) {
+                case 0: off = sw.run<false, false, false>(sf4, js, 0, j_full, off); off = sw.run<true, false, false>(sf4, js, j_full, j_diag, off); break;
+                case 1: off = sw.run<false, true, false>(sf4, js, 0, j_full, off); off = sw.run<true, true, false>(sf4, js, j_full, j_diag, off); break;
+                case 2: off = sw.run<false, false, true>(sf4, js, 0, j_full, off); off = sw.run<true, false, true>(sf4, js, j_full, j_diag, off); break;
+                default: off = sw.run<false, true, true>(sf4, js, 0, j_full, off); off = sw.run<true, true, true>(sf4, js, j_full, j_diag, off); break;
             }
         }
     }
@@ -755,7 +786,7 @@ static int launch_mch(const AtomArgs<T>& a, int max_members, cudaStream_t st) {
 
 template <typename T>
 static int launch_filter(const AtomArgs<T>& a, cudaStream_t st) {
-    const size_t smem = (size_t)kFilterWarps * a.scap * sizeof(float4);
+    const size_t smem = (size_t)kFilterWarps * (a.scap + 1) * sizeof(float4);
     auto kern = pair_filter_kernel<T>;
     static size_t configured = 0;
     if (smem > configured) {
