@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--atoms", type=int, default=int(os.environ.get("PANTEA_BENCH_ATOMS", "100000")))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-times", action="store_true",
+                    help="after the timed region, print a per-kernel breakdown (CUPTI, diagnostic only) to stderr")
     ap.add_argument("--no-flush", action="store_true", help="diagnostics only: skip the L2 flush between steps")
     args = ap.parse_args()
     args.atoms = 3 * (args.atoms // 3)  # whole water molecules: "100 000 atoms" = 33 333 molecules = 99 999 atoms
@@ -221,6 +223,18 @@ def run_b200(args) -> None:
     ms_total = float(ms_t.item())
     clocks = sampler.stop() if sampler else None
     value = n * args.steps / (ms_total * 1e-3)
+
+    if args.kernel_times and rank == 0:  # diagnostic: never feeds a reported number
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(5):
+                flush()
+                md.step()
+            torch.cuda.synchronize()
+        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:12]
+        for e in rows:
+            print(f"[kernel-times] {e.key[:70]:70s} n={e.count:4d} avg={e.device_time_total / e.count / 1e3:8.4f} ms",
+                  file=sys.stderr)
 
     # ---- neighbour-capacity check after the run (the timed loop never synchronises) ------------------
     mx = C.c_int32(0)

@@ -159,6 +159,8 @@ struct pantea_workspace {
 
     // device buffers
     void* rec = nullptr;           // Rec<T>[max_atoms]
+    void* rec_screen = nullptr;    // Rec<float>[max_atoms]: box-wrapped positions for the FP32 screening pass (F64 cell mode)
+    int32_t* wide_flag = nullptr;  // [1] set when an atom lies more than a quarter box outside the cell
     int32_t* slot_of = nullptr;    // [max_atoms] original index -> sorted slot
     int32_t* struct_of = nullptr;  // [max_atoms] structure id per sorted slot (batch mode)
     int32_t* nbr = nullptr;        // [max_atoms * cap] sorted-slot indices, partitioned by bucket

@@ -37,10 +37,17 @@ __device__ __forceinline__ int cell_coord(double x, double inv, int n) {
 // binning
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void cell_assign_kernel(const T* __restrict__ pos, int n, CellArg ca, int32_t* __restrict__ cell_of,
-                                   int32_t* __restrict__ cell_count) {
+__global__ void cell_assign_kernel(const T* __restrict__ pos, int n, CellArg ca, BoxArg box, int32_t* __restrict__ cell_of,
+                                   int32_t* __restrict__ cell_count, int32_t* __restrict__ wide_flag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    {   // the screening pass measures true minimum-image distances; they equal the reference's single-shift ones only
+        // while every coordinate difference stays below 1.5 box lengths
+        const double x = (double)pos[3 * i], y = (double)pos[3 * i + 1], z = (double)pos[3 * i + 2];
+        const bool wide = !(x >= -0.25 * box.lx && x <= 1.25 * box.lx && y >= -0.25 * box.ly && y <= 1.25 * box.ly &&
+                            z >= -0.25 * box.lz && z <= 1.25 * box.lz);
+        if (wide) *wide_flag = 1;
+    }
     int cx = cell_coord((double)pos[3 * i], ca.inv_x, ca.nx);
     int cy = cell_coord((double)pos[3 * i + 1], ca.inv_y, ca.ny);
     int cz = cell_coord((double)pos[3 * i + 2], ca.inv_z, ca.nz);
@@ -105,7 +112,7 @@ template <typename T>
 __global__ void cell_sort_pack_kernel(const T* __restrict__ pos, const int32_t* __restrict__ types, int n_types,
                                       const int32_t* __restrict__ cell_start, int ncells,
                                       const int32_t* __restrict__ tmp_order, Rec<T>* __restrict__ rec,
-                                      int32_t* __restrict__ slot_of) {
+                                      int32_t* __restrict__ slot_of, Rec<float>* __restrict__ rec_screen, BoxArg box) {
     int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (cell >= ncells) return;
@@ -119,6 +126,15 @@ __global__ void cell_sort_pack_kernel(const T* __restrict__ pos, const int32_t* 
         rec_set(r, bucket_of(types[mine], n_types), mine);
         rec[lo + rank] = r;
         slot_of[mine] = lo + rank;
+        if (rec_screen) {  // box-wrapped coordinates in [0, L], rounded to float
+            const double x = (double)r.x, y = (double)r.y, z = (double)r.z;
+            Rec<float> f;
+            f.x = (float)(x - box.lx * floor(x / box.lx));
+            f.y = (float)(y - box.ly * floor(y / box.ly));
+            f.z = (float)(z - box.lz * floor(z / box.lz));
+            rec_set(f, bucket_of(types[mine], n_types), mine);
+            rec_screen[lo + rank] = f;
+        }
     }
 }
 
@@ -162,6 +178,9 @@ struct RowArgs {
     int32_t* nbr;
     int32_t* tcount;
     int32_t* flags;
+    const Rec<float>* rec_screen;  // FP32 screening records (F64 cell mode) or NULL
+    const int32_t* wide_flag;
+    float screen_band;             // |r2_f32 - r2| bound around rc^2 (and around 0)
 };
 
 template <typename T, int MODE>
@@ -214,6 +233,47 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) neighbor_rows_kernel(cons
         }
     };
 
+    // FP32 screening (F64 workspaces, cell mode): |d| per axis is min(|dx|, L - |dx|) on box-wrapped single-precision
+    // coordinates; only candidates whose r^2 falls within the error band of rc^2 (or of 0) take the exact path above.
+    // The accepted set is therefore identical to the exact predicate's.
+    const bool screen = sizeof(T) == 8 && MODE == kModeCell && a.rec_screen != nullptr && *a.wide_flag == 0;
+    Rec<float> rif;
+    rif.x = rif.y = rif.z = 0.f;
+    if (screen) rif = a.rec_screen[i];
+    const float flx = (float)a.box.lx, fly = (float)a.box.ly, flz = (float)a.box.lz;
+    const float rc2f = (float)(a.rc * a.rc), lo_f = rc2f - a.screen_band, hi_f = rc2f + a.screen_band;
+    auto scan_screen = [&](int lo, int hi) {
+        for (int j0 = lo; j0 < hi; j0 += 32) {
+            const int j = j0 + lane;
+            bool ok = false;
+            int bucket = 0;
+            if (j < hi) {
+                const Rec<float> rj = a.rec_screen[j];
+                float ax = fabsf(rif.x - rj.x), ay = fabsf(rif.y - rj.y), az = fabsf(rif.z - rj.z);
+                ax = fminf(ax, flx - ax); ay = fminf(ay, fly - ay); az = fminf(az, flz - az);
+                const float r2f = ax * ax + ay * ay + az * az;
+                ok = r2f < lo_f;
+                const bool ambiguous = (ok ? r2f <= a.screen_band : r2f <= hi_f) && j != i;
+                if (j == i) ok = false;
+                if (ambiguous) {
+                    const Rec<T> rj = rec[j];
+                    T dx = sub_rn(ri.x, rj.x), dy = sub_rn(ri.y, rj.y), dz = sub_rn(ri.z, rj.z);
+                    dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz);
+                    const T r = norm3_rn(dx, dy, dz);
+                    ok = (r <= rc) && (r > (T)0);
+                }
+                bucket = rec_type(rj);
+            }
+            const unsigned m = __ballot_sync(kFull, ok);
+            const int p = cnt + __popc(m & ((1u << lane) - 1u));
+            if (ok && p < a.cap) L[p] = j | (bucket << 28);
+            cnt += __popc(m);
+        }
+    };
+    auto scan_any = [&](int lo, int hi) {
+        if (screen) scan_screen(lo, hi); else scan(lo, hi);
+    };
+
     if (MODE == kModeCell) {
         int cx = cell_coord((double)ri.x, a.cell.inv_x, a.cell.nx);
         int cy = cell_coord((double)ri.y, a.cell.inv_y, a.cell.ny);
@@ -225,11 +285,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) neighbor_rows_kernel(cons
                 int rowc = (z * a.cell.ny + y) * a.cell.nx;
                 // the three x-cells are contiguous in memory unless the stencil wraps around
                 if (cx > 0 && cx < a.cell.nx - 1) {
-                    scan(a.cell_start[rowc + cx - 1], a.cell_start[rowc + cx + 2]);
+                    scan_any(a.cell_start[rowc + cx - 1], a.cell_start[rowc + cx + 2]);
                 } else {
                     for (int dx = -1; dx <= 1; ++dx) {
                         int x = cx + dx; x = x < 0 ? x + a.cell.nx : (x >= a.cell.nx ? x - a.cell.nx : x);
-                        scan(a.cell_start[rowc + x], a.cell_start[rowc + x + 1]);
+                        scan_any(a.cell_start[rowc + x], a.cell_start[rowc + x + 1]);
                     }
                 }
             }
@@ -377,7 +437,8 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
         if (rcode != PANTEA_OK) return rcode;
         ws->mode = kModeCell;
         PANTEA_CUDA_TRY(cudaMemsetAsync(ws->cell_fill, 0, 4 * (ncells + 1), st));
-        cell_assign_kernel<T><<<blocks_n, threads, 0, st>>>(pos, (int)n, ca, ws->cell_of, ws->cell_fill);
+        PANTEA_CUDA_TRY(cudaMemsetAsync(ws->wide_flag, 0, 4, st));
+        cell_assign_kernel<T><<<blocks_n, threads, 0, st>>>(pos, (int)n, ca, ba, ws->cell_of, ws->cell_fill, ws->wide_flag);
         PANTEA_LAUNCH_CHECK();
         cell_scan_kernel<<<1, 1024, 0, st>>>(ws->cell_fill, (int)ncells, ws->cell_start, ws->cell_fill);
         PANTEA_LAUNCH_CHECK();
@@ -385,7 +446,8 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
         PANTEA_LAUNCH_CHECK();
         const int blocks_c = (int)((ncells * 32 + threads - 1) / threads);
         cell_sort_pack_kernel<T><<<blocks_c, threads, 0, st>>>(pos, types, ws->n_types, ws->cell_start, (int)ncells,
-                                                               ws->tmp_order, rec, ws->slot_of);
+                                                               ws->tmp_order, rec, ws->slot_of,
+                                                               (Rec<float>*)ws->rec_screen, ba);
         PANTEA_LAUNCH_CHECK();
     } else {
         ws->mode = kModeAllPairs;
@@ -399,6 +461,14 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
     ra.struct_ptr = struct_ptr; ra.boxes = boxes; ra.rc = rc;
     ra.own_begin = (int)ws->own_begin; ra.own_end = ws->own_end < 0 ? (int)n : (int)ws->own_end;
     ra.nbr = ws->nbr; ra.tcount = ws->nbr_tcount; ra.flags = ws->flags;
+    ra.rec_screen = use_cells ? (const Rec<float>*)ws->rec_screen : nullptr;
+    ra.wide_flag = ws->wide_flag;
+    {   // error bound of the screening distance (see neighbor_rows_kernel): per-axis |error| <= 5 L 2^-24, squared
+        // distance |error| <= 2 sqrt(3) r delta + 3 delta^2 + 4 2^-24 r^2 at r ~ rc; doubled for safety
+        const double lmax = std::max(ws->box[0], std::max(ws->box[1], ws->box[2]));
+        const double delta = 5.0 * lmax * 5.9604644775390625e-08;
+        ra.screen_band = (float)(2.0 * (3.5 * rc * delta + 3.0 * delta * delta + 3.0e-7 * rc * rc));
+    }
     const int blocks_w = (int)((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
     const size_t smem = (size_t)kWarpsPerBlock * ws->cap * sizeof(int32_t);
     if (use_cells)

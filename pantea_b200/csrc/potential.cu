@@ -214,6 +214,8 @@ int pantea_workspace_create(const pantea_potential* pot, int64_t max_atoms, int3
         if (err == cudaSuccess) err = cudaMalloc(p, bytes);
     };
     alloc(&ws->rec, rsz * max_atoms);
+    if (dtype == PANTEA_F64) alloc(&ws->rec_screen, sizeof(Rec<float>) * max_atoms);
+    alloc((void**)&ws->wide_flag, 4);
     alloc((void**)&ws->slot_of, 4 * max_atoms);
     alloc((void**)&ws->struct_of, 4 * max_atoms);
     alloc((void**)&ws->nbr, 4 * (size_t)max_atoms * ws->cap);
@@ -242,7 +244,7 @@ int pantea_workspace_destroy(pantea_workspace* ws) {
     if (ws->capture_stream) cudaStreamDestroy(ws->capture_stream);
     void* ptrs[] = {ws->rec, ws->slot_of, ws->struct_of, ws->nbr, ws->nbr_tcount, ws->cell_of, ws->tmp_order,
                     ws->cell_start, ws->cell_fill, ws->flags, ws->e_partial, ws->md_forces, ws->md_eatom, ws->md_ke,
-                    ws->pairs, ws->pair_off, ws->gbuf};
+                    ws->pairs, ws->pair_off, ws->gbuf, ws->rec_screen, ws->wide_flag};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete ws;
