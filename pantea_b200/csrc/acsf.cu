@@ -318,7 +318,7 @@ struct NbrBlock {
 };
 
 // One angular group (same neighbour types, cutoff and kind), members [m0, m0 + mc), flat over the pair list.
-// FAST: compile-time specialisation for the common RuNNer setting -- G3, tanhu cutoff, zeta == 1 for every member
+// FAST: compile-time specialisation for the common RuNNer setting -- G3, tanhu cutoff, integer zeta >= 1 for every member
 // -- whose triplet body is straight-line code; otherwise kind / cutoff / zeta are runtime (warp-uniform) branches.
 template <typename T, int WPA, bool GRAD, int MCH, bool FAST>
 __device__ __forceinline__ void angular_group(const ElementTable& tab, const AngularGroup& grp, int m0, int mc,
@@ -434,7 +434,8 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
                     for (int u = 0; u < NU; ++u) {
                         const T bs = (T)1 + m_lam[m] * cost[u];
                         T pw1 = (T)1;
-                        if (!FAST && m_iz[m] != 1) pw1 = m_iz[m] > 1 ? powi<T>(bs, m_iz[m] - 1) : pow_general<T>(bs, m_zm1[m]);
+                        if (m_iz[m] != 1)  // warp-uniform; FAST groups only hold integer zeta >= 1
+                            pw1 = (FAST || m_iz[m] > 1) ? powi<T>(bs, m_iz[m] - 1) : pow_general<T>(bs, m_zm1[m]);
                         const T ep = e[u] * fprod[u] * pw1;
                         const T ap = m_pref[m] * bs * ep;  // this triplet's contribution to G
                         aG[m] += ap;
@@ -589,7 +590,7 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
             const int lo = offs[gi], count = offs[gi + 1] - lo;
             NbrBlock<T> nb{snb, stride, 5 + 2 * grp.cls};
             bool fast = tab.cls[grp.cls].type == PANTEA_CUT_TANHU && grp.kind == PANTEA_G3;
-            for (int m = 0; m < grp.count; ++m) fast = fast && tab.members[grp.first + m].izeta == 1;
+            for (int m = 0; m < grp.count; ++m) fast = fast && tab.members[grp.first + m].izeta >= 1;
             for (int m0 = 0; m0 < grp.count; m0 += MCH) {
                 const int mc = grp.count - m0 < MCH ? grp.count - m0 : MCH;
                 if (fast)

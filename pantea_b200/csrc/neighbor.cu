@@ -12,6 +12,9 @@
 namespace pantea {
 
 constexpr int kWarpsPerBlock = 8;
+#ifndef PANTEA_ROWS_MINBLOCKS
+#define PANTEA_ROWS_MINBLOCKS 4
+#endif
 constexpr unsigned kFull = 0xffffffffu;
 
 struct BoxArg {
@@ -28,8 +31,10 @@ __device__ __forceinline__ int bucket_of(int type, int n_types) { return (type >
 
 __device__ __forceinline__ int cell_coord(double x, double inv, int n) {
     int c = (int)floor(x * inv);
-    c %= n;
-    if (c < 0) c += n;
+    if ((unsigned)c >= (unsigned)n) {  // outside the box: wrap (the integer division stays off the common path)
+        c %= n;
+        if (c < 0) c += n;
+    }
     return c;
 }
 
@@ -184,7 +189,7 @@ struct RowArgs {
 };
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) neighbor_rows_kernel(const Rec<T>* __restrict__ rec, RowArgs a) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, PANTEA_ROWS_MINBLOCKS) neighbor_rows_kernel(const Rec<T>* __restrict__ rec, RowArgs a) {
     extern __shared__ int32_t smem_rows[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int i = blockIdx.x * kWarpsPerBlock + wib;
@@ -309,7 +314,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) neighbor_rows_kernel(cons
         int e = e0 + lane;
         int bk = e < total ? (int)((unsigned)L[e] >> 28) : -1;
 #pragma unroll
-        for (int b = 0; b < kBuckets; ++b) c[b] += __popc(__ballot_sync(kFull, bk == b));
+        for (int b = 0; b < kBuckets; ++b) {
+            if (b >= a.n_buckets) break;  // warp-uniform: only the potential's element buckets (+ "other") are in use
+            c[b] += __popc(__ballot_sync(kFull, bk == b));
+        }
     }
     int run[kBuckets];
     int acc = 0;
@@ -323,6 +331,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) neighbor_rows_kernel(cons
         int dst = -1;
 #pragma unroll
         for (int b = 0; b < kBuckets; ++b) {
+            if (b >= a.n_buckets) break;
             unsigned m = __ballot_sync(kFull, bk == b);
             if (bk == b) dst = run[b] + __popc(m & ((1u << lane) - 1u));
             run[b] += __popc(m);
