@@ -100,7 +100,12 @@ __device__ __forceinline__ double fast_rcp(double a) {  // 1/a for normal positi
     e = fma(-a, r, 1.0);
     return fma(r, e, r);
 }
-__device__ __forceinline__ float fast_rcp(float a) { return __frcp_rn(a); }
+// FP32 mode (tolerance 1e-5): the hardware approximations (MUFU, ~1-2 ulp) are used directly
+__device__ __forceinline__ float fast_rcp(float a) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
 
 __device__ __forceinline__ double fast_sqrt(double a) {  // sqrt(a) for normal positive a
     double y;
@@ -112,7 +117,11 @@ __device__ __forceinline__ double fast_sqrt(double a) {  // sqrt(a) for normal p
     double s = a * y;
     return fma(0.5 * y, fma(-s, s, a), s);   // one correction step on the root itself
 }
-__device__ __forceinline__ float fast_sqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ float fast_sqrt(float a) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
 // 1/sqrt(a) for normal positive a, ~2 ulp
 __device__ __forceinline__ double fast_rsqrt(double a) {
     double y;
@@ -122,7 +131,11 @@ __device__ __forceinline__ double fast_rsqrt(double a) {
     e = fma(-a * y, y, 1.0);
     return fma(0.5 * y, e, y);
 }
-__device__ __forceinline__ float fast_rsqrt(float a) { return 1.0f / __fsqrt_rn(a); }
+__device__ __forceinline__ float fast_rsqrt(float a) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
 // triplet-loop variant: two Newton steps on the reciprocal root already reach ~2 ulp, the final correction is dropped;
 // a == 0 yields NaN (the caller's comparison then rejects the lane)
 __device__ __forceinline__ double fast_sqrt_loop(double a) {
@@ -134,7 +147,7 @@ __device__ __forceinline__ double fast_sqrt_loop(double a) {
     y = fma(0.5 * y, e, y);
     return a * y;
 }
-__device__ __forceinline__ float fast_sqrt_loop(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ float fast_sqrt_loop(float a) { return fast_sqrt(a); }
 
 // Taylor coefficients 1/n!, n = 0..12, in constant memory so that they fold into the FMA operands
 static __constant__ double kExpC[13] = {
@@ -192,7 +205,7 @@ __device__ __forceinline__ double fast_exp_tab(double y, const double* __restric
     return __hiloint2double(under ? 0 : hi, under ? 0 : lo);
 }
 template <bool CLAMP>
-__device__ __forceinline__ float fast_exp_tab(float y, const float*) { return expf(y); }
+__device__ __forceinline__ float fast_exp_tab(float y, const float*) { return __expf(y); }
 // tanh(x), x in [0, ~20], through the table-driven exponential
 template <typename T>
 __device__ __forceinline__ T fast_tanh_pos_tab(T x, const T* __restrict__ tab) {
@@ -201,8 +214,8 @@ __device__ __forceinline__ T fast_tanh_pos_tab(T x, const T* __restrict__ tab) {
 
 __device__ __forceinline__ double fast_exp(double y) { return fast_exp_t<true>(y); }
 __device__ __forceinline__ double fast_exp_small(double y) { return fast_exp_t<false>(y); }
-__device__ __forceinline__ float fast_exp_small(float y) { return expf(y); }
-__device__ __forceinline__ float fast_exp(float y) { return expf(y); }
+__device__ __forceinline__ float fast_exp_small(float y) { return __expf(y); }
+__device__ __forceinline__ float fast_exp(float y) { return __expf(y); }
 
 __device__ __forceinline__ double cospi_t(double x) { return cospi(x); }
 __device__ __forceinline__ float cospi_t(float x) { return cospif(x); }
