@@ -31,7 +31,10 @@
 namespace pantea {
 
 constexpr unsigned kFullMask = 0xffffffffu;
-constexpr int kAtomsPerBlock = 4;   // eval kernel, WPA == 1 configuration: 4 warps, one atom each
+constexpr int kEvalWarps = 4;       // eval kernel: 4 warps per block, shared by 4 / WPA atoms (WPA = warps per atom)
+#ifndef PANTEA_EVAL_WPA
+#define PANTEA_EVAL_WPA 1           // warps per atom when there are enough atoms to fill the GPU
+#endif
 constexpr int kFilterWarps = 8;     // pair filter: 8 warps per block, one atom each
 constexpr int kNU = PANTEA_TRIPLETS_PER_LANE;
 #ifndef PANTEA_STAGE_ITERS
@@ -114,10 +117,12 @@ __device__ __noinline__ void activation_eval_ool(int act, T x, T* y, T* dy) {
     *y = a; *dy = b;
 }
 
+// barrier over the WPA warps of one atom (several atoms share a block: named barriers 1.., one per atom)
 template <int WPA>
-__device__ __forceinline__ void group_sync() {
+__device__ __forceinline__ void group_sync(int atom_in_block) {
     if (WPA == 1) __syncwarp();
-    else __syncthreads();
+    else if (WPA == kEvalWarps) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(atom_in_block + 1), "n"(WPA * 32) : "memory");
 }
 
 // work item -> (cell-ordered slot, output row, element table); false when the item is not evaluated
@@ -320,7 +325,7 @@ struct NbrBlock {
 // One angular group (same neighbour types, cutoff and kind), members [m0, m0 + mc), flat over the pair list.
 // FAST: compile-time specialisation for the common RuNNer setting -- G3, tanhu cutoff, integer zeta >= 1 for every member
 // -- whose triplet body is straight-line code; otherwise kind / cutoff / zeta are runtime (warp-uniform) branches.
-template <typename T, int WPA, bool GRAD, int MCH, bool FAST>
+template <typename T, int WPA, bool GRAD, int MCH, bool FAST, bool COUNT>
 __device__ __forceinline__ void angular_group(const ElementTable& tab, const AngularGroup& grp, int m0, int mc,
                                               const NbrBlock<T>& nb, const int32_t* __restrict__ list, int count,
                                               bool wrap_jk, T lx, T ly, T lz, int lane, int tid_atom, T* my_acc,
@@ -329,7 +334,7 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
     constexpr int S = 32 * WPA;
     const int ctype = tab.cls[grp.cls].type;
     const T rc = (T)tab.cls[grp.cls].rc;
-    const T inv_rc = (T)1 / rc;
+    const T inv_rc = (T)1 / rc, m2_inv_rc = (T)-2 / rc;
     const bool is_g3 = FAST ? true : grp.kind == PANTEA_G3;
 
     T m_neta[MCH], m_2neta[MCH], m_lam[MCH], m_zl[MCH], m_pref[MCH], m_zm1[MCH];
@@ -351,7 +356,6 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
     constexpr int CH = kStageIters;
     const int n_iter = (count + S * NU - 1) / (S * NU);
     const int n_chunks = (n_iter + CH - 1) / CH;
-    const bool counting = cnt_trip != ~0ull;
     auto stage_chunk = [&](int chunk) {  // entries past the end re-read entry 0: every lane always holds a real pair
         int* dst = stage + (chunk & 1) * (CH * NU * 32) + lane;
         int e = chunk * (CH * NU * S) + tid_atom;
@@ -400,7 +404,7 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
 #pragma unroll
                 for (int u = 0; u < NU; ++u) rjk[u] = fast_sqrt_loop(rjk2[u]);
 #pragma unroll
-                for (int u = 0; u < NU; ++u) t[u] = fast_tanh_pos_tab<T>((T)1 - rjk[u] * inv_rc, etab);
+                for (int u = 0; u < NU; ++u) t[u] = fast_tanh_half_tab<T>(fma(rjk[u], m2_inv_rc, (T)2), etab);
 #pragma unroll
                 for (int u = 0; u < NU; ++u) {
                     fcjk[u] = (valid[u] && rjk[u] < rc) ? t[u] * t[u] * t[u] : (T)0;
@@ -443,14 +447,14 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
                             const T Tc = m_zl[m] * ep;
                             const T Bj = Tc * (ivk[u] - cost[u] * ivj[u]) + ap * (qj[u] + m_2neta[m] * rj[u]);
                             const T Bk = Tc * (ivj[u] - cost[u] * ivk[u]) + ap * (qk[u] + m_2neta[m] * rk[u]);
-                            aX[m] += Bj * uxj[u] + Bk * uxk[u];
-                            aY[m] += Bj * uyj[u] + Bk * uyk[u];
-                            aZ[m] += Bj * uzj[u] + Bk * uzk[u];
+                            aX[m] = fma(Bk, uxk[u], fma(Bj, uxj[u], aX[m]));
+                            aY[m] = fma(Bk, uyk[u], fma(Bj, uyj[u], aY[m]));
+                            aZ[m] = fma(Bk, uzk[u], fma(Bj, uzj[u], aZ[m]));
                         }
                     }
                 }
             }
-            if (counting) {
+            if (COUNT && cnt_trip != ~0ull) {
 #pragma unroll
                 for (int u = 0; u < NU; ++u) cnt_trip += (valid[u] && fcjk[u] != (T)0) ? (unsigned long long)mc : 0ull;
             }
@@ -471,19 +475,20 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
 }
 
 template <typename T, int WPA, bool GRAD, int MCH>
-__global__ void __launch_bounds__(WPA == 1 ? kAtomsPerBlock * 32 : WPA * 32, (sizeof(T) == 8 && GRAD) ? PANTEA_EVAL_MINBLOCKS : 1)
+__global__ void __launch_bounds__(kEvalWarps * 32, (sizeof(T) == 8 && GRAD) ? PANTEA_EVAL_MINBLOCKS : 1)
 hdnnp_eval_kernel(const AtomArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int atom_in_block = WPA == 1 ? wib : 0;
-    const int wrank = WPA == 1 ? 0 : wib;           // rank of this warp among the atom's warps
+    constexpr int APB = kEvalWarps / WPA;           // atoms per block
+    const int atom_in_block = wib / WPA;
+    const int wrank = wib % WPA;                    // rank of this warp among the atom's warps
     const int tid_atom = wrank * 32 + lane;         // thread index within the atom group
     constexpr int S = 32 * WPA;                     // threads per atom
     __shared__ T s_etab[64];                        // 2^(i/64) for the table-driven exponential
     exp2_table_fill(s_etab, threadIdx.x, blockDim.x);
     __shared__ int s_stage[4][2 * kStageIters * kNU * 32];  // per-warp pair-list staging ring (128 threads per block)
     __syncthreads();
-    const int w = blockIdx.x * (WPA == 1 ? kAtomsPerBlock : 1) + atom_in_block;
+    const int w = blockIdx.x * APB + atom_in_block;
     if (w >= a.n_work) return;
 
     int slot, out_row, etype;
@@ -551,7 +556,7 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
             }
         }
     }
-    group_sync<WPA>();
+    group_sync<WPA>(atom_in_block);
 
     T* my_acc = sacc + (size_t)wrank * a.n_sf_max * 4;
     unsigned long long cnt_rad = 0, cnt_trip = a.counters ? 0ull : ~0ull;  // work counters (~0: disabled)
@@ -593,12 +598,16 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
             for (int m = 0; m < grp.count; ++m) fast = fast && tab.members[grp.first + m].izeta >= 1;
             for (int m0 = 0; m0 < grp.count; m0 += MCH) {
                 const int mc = grp.count - m0 < MCH ? grp.count - m0 : MCH;
-                if (fast)
-                    angular_group<T, WPA, GRAD, MCH, true>(tab, grp, m0, mc, nb, lists + lo, count, wrap_jk, lx, ly, lz, lane,
-                                                           tid_atom, my_acc, s_etab, s_stage[threadIdx.x >> 5], cnt_trip);
+                // the work counters (bench / roofline pass only) are compiled out of the common fast variant
+                if (fast && cnt_trip == ~0ull)
+                    angular_group<T, WPA, GRAD, MCH, true, false>(tab, grp, m0, mc, nb, lists + lo, count, wrap_jk, lx, ly, lz,
+                                                                  lane, tid_atom, my_acc, s_etab, s_stage[threadIdx.x >> 5], cnt_trip);
+                else if (fast)
+                    angular_group<T, WPA, GRAD, MCH, true, true>(tab, grp, m0, mc, nb, lists + lo, count, wrap_jk, lx, ly, lz,
+                                                                 lane, tid_atom, my_acc, s_etab, s_stage[threadIdx.x >> 5], cnt_trip);
                 else
-                    angular_group<T, WPA, GRAD, MCH, false>(tab, grp, m0, mc, nb, lists + lo, count, wrap_jk, lx, ly, lz, lane,
-                                                            tid_atom, my_acc, s_etab, s_stage[threadIdx.x >> 5], cnt_trip);
+                    angular_group<T, WPA, GRAD, MCH, false, true>(tab, grp, m0, mc, nb, lists + lo, count, wrap_jk, lx, ly, lz,
+                                                                  lane, tid_atom, my_acc, s_etab, s_stage[threadIdx.x >> 5], cnt_trip);
             }
         }
     }
@@ -610,7 +619,7 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
             atomicAdd(&a.counters[2], cnt_trip);
         }
     }
-    group_sync<WPA>();
+    group_sync<WPA>(atom_in_block);
     if (wrank != 0) return;  // the atom's first warp finishes the job
 
     // ---- combine the warps' partial sums (fixed order) -------------------------------------------
@@ -764,7 +773,7 @@ static int g_num_sms = 0;
 
 template <typename T, int WPA, bool GRAD, int MCH>
 static int launch_eval(const AtomArgs<T>& args, cudaStream_t st) {
-    const int apb = WPA == 1 ? kAtomsPerBlock : 1;
+    const int apb = kEvalWarps / WPA;
     const size_t smem = apb * eval_smem_bytes<T>(args.scap, args.n_cls_max, args.n_sf_max, args.n_neurons_max, args.width_max, WPA);
     auto kern = hdnnp_eval_kernel<T, WPA, GRAD, MCH>;
     static size_t configured = 0;  // per instantiation
@@ -873,7 +882,7 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
     // few atoms: several warps per atom so that every SM sub-partition has work
     const bool wide = (int64_t)a.n_work < (int64_t)g_num_sms * 64;
     if (wide) rc = grad ? launch_mch<T, 4, true>(a, mm, st) : launch_mch<T, 4, false>(a, mm, st);
-    else rc = grad ? launch_mch<T, 1, true>(a, mm, st) : launch_mch<T, 1, false>(a, mm, st);
+    else rc = grad ? launch_mch<T, PANTEA_EVAL_WPA, true>(a, mm, st) : launch_mch<T, PANTEA_EVAL_WPA, false>(a, mm, st);
     if (rc != PANTEA_OK || !a.gbuf) return rc;
     {
         const int gw = a.width_max > a.n_sf_max ? a.width_max : a.n_sf_max;

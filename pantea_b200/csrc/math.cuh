@@ -206,6 +206,11 @@ __device__ __forceinline__ double fast_exp_tab(double y, const double* __restric
 }
 template <bool CLAMP>
 __device__ __forceinline__ float fast_exp_tab(float y, const float*) { return __expf(y); }
+// tanh(y / 2), y in [0, ~40], through the table-driven exponential: 1 - 2 / (exp(y) + 1)
+template <typename T>
+__device__ __forceinline__ T fast_tanh_half_tab(T y, const T* __restrict__ tab) {
+    return fma((T)-2, fast_rcp(fast_exp_tab<false>(y, tab) + (T)1), (T)1);
+}
 // tanh(x), x in [0, ~20], through the table-driven exponential
 template <typename T>
 __device__ __forceinline__ T fast_tanh_pos_tab(T x, const T* __restrict__ tab) {
