@@ -120,6 +120,23 @@ class ReplicatedMD:
         self._bind(check=True)
         self._forces(self.frc)
 
+    def reset(self, positions: torch.Tensor, velocities: torch.Tensor) -> None:
+        """Restart from the given state (same atoms, box and potential): positions, velocities, forces."""
+        self.pos.copy_(positions)
+        self.vel.copy_(velocities)
+        self.steps = 0
+        self._bind()
+        self._forces(self.frc)
+
+    def check_capacity(self) -> int:
+        """Read (and reset) the sticky device-side capacity flags; raises CapacityError after enlarging the buffers when
+        a neighbour row, the staged neighbour block or a pair list overflowed since the last call.  Returns the largest
+        neighbour count seen."""
+        import ctypes as C
+        mx = C.c_int32(0)
+        self._lib.check(self.lib.pantea_neighbor_status(self.ws.handle, C.byref(mx), self._lib.stream_ptr()))
+        return int(mx.value)
+
     def _bind(self, check: bool = False) -> None:
         self.ws.bind(self.pos, self.types, self.box, self.pot.r_cutoff, check=check, owned=(self.lo, self.hi))
 
