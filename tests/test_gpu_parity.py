@@ -61,6 +61,64 @@ def test_neighbor_sets_bit_exact(n_atoms, rc, use_box, h2o):
     assert np.array_equal(col.cpu().numpy(), col_o)
 
 
+def _assert_sets_equal(pos, types, box, rc, cap=None):
+    row_ptr_o, col_o = c_oracle.neighbors(pos, types, box, rc)
+    n = len(pos)
+    ws = _workspace(None, n, cap=cap)
+    ws.bind(cuda(pos), cuda(types, torch.int32), box, rc)
+    row_ptr, col = ws.neighbor_lists()
+    assert np.array_equal(row_ptr.cpu().numpy(), row_ptr_o)
+    assert np.array_equal(col.cpu().numpy(), col_o)
+    return row_ptr_o
+
+
+def test_neighbor_sets_distances_exactly_at_cutoff():
+    """Simple-cubic lattice, spacing 3 Bohr, rc = 12: (4,0,0)a lies exactly on the cutoff sphere (included: r <= rc),
+    and a copy of the lattice nudged by single ulps puts pairs one rounding step either side of it."""
+    m, a, rc = 15, 3.0, 12.0
+    g = np.arange(m, dtype=np.float64) * a
+    pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    types = np.where(np.arange(len(pos)) % 3 == 0, 2, 1).astype(np.int32)
+    box = np.array([m * a] * 3)
+    rp = _assert_sets_equal(pos, types, box, rc, cap=320)
+    assert (np.diff(rp) == 256).all()  # 257 lattice points within the closed ball, minus the atom itself
+    rng = np.random.default_rng(5)
+    nudged = pos.copy()
+    sel = rng.random(len(pos)) < 0.5
+    nudged[sel] = np.nextafter(nudged[sel], np.where(rng.random((sel.sum(), 3)) < 0.5, -np.inf, np.inf))
+    _assert_sets_equal(nudged, types, box, rc, cap=320)
+
+
+@pytest.mark.parametrize("shift,frac", [(0.2, 1.0), (-0.2, 1.0), (0.6, 0.3), (3.3, 0.05), (-1.7, 1.0)])
+def test_neighbor_sets_atoms_outside_the_box(shift, frac):
+    """The reference applies one box shift to raw coordinate differences (box.py:112-117); atoms far outside the cell
+    therefore lose neighbours.  The FP32 screening pass measures true minimum-image distances and must hand over to
+    the exact scan exactly when the two notions can differ."""
+    pos, types, box = water_box(3000)
+    rng = np.random.default_rng(11)
+    moved = rng.random(len(pos)) < frac
+    pos = pos.copy()
+    pos[moved] += shift * box
+    _assert_sets_equal(pos, types, box, 12.0)
+
+
+def test_neighbor_sets_pairs_within_rounding_of_cutoff_in_a_large_box():
+    """Pairs at r = rc (1 + delta), |delta| from 1e-15 to 1e-4, at coordinates up to 400 Bohr: the FP32 screen (absolute
+    coordinate error ~2e-5 Bohr here) must route every one of them through the exact FP64 predicate."""
+    rng = np.random.default_rng(17)
+    L, rc = 400.0, 12.0
+    deltas = np.array([0.0, 1e-15, -1e-15, 1e-13, -1e-13, 1e-10, -1e-10, 1e-8, -1e-8, 1e-7, -1e-7, 1e-6, -1e-6, 1e-5, -1e-5,
+                       1e-4, -1e-4, 1e-3, -1e-3])
+    sites = rng.random((40 * len(deltas), 3)) * L
+    u = rng.standard_normal(sites.shape)
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    partner = np.remainder(sites + rc * (1.0 + np.tile(deltas, 40))[:, None] * u, L)
+    filler = rng.random((1500, 3)) * L
+    pos = np.concatenate([sites, partner, filler])
+    types = rng.integers(1, 3, len(pos)).astype(np.int32)
+    _assert_sets_equal(pos, types, np.array([L, L, L]), rc, cap=64)
+
+
 def test_neighbor_capacity_overflow_is_reported_and_grown():
     from pantea_b200 import _lib, engine
     pos, types, box = water_box(192)
