@@ -210,6 +210,18 @@ int pantea_l2_flush(void* scratch, int64_t bytes, void* stream);
    [2] triplet-SF evaluations -- accumulated by every later descriptor / energy launch of `ws` */
 int pantea_workspace_set_counters(pantea_workspace* ws, void* counters);
 
+/* Verlet-skin reuse of the neighbour rows and pair lists (the reference notes the missing
+   feature in atoms/neighbor.py:34-36).  With skin > 0 and a periodic cell-list build, pantea_neighbor_build gathers
+   rows with radius r_cutoff + skin and later calls with the same atoms / box / cutoff rebuild them only when some atom
+   has moved more than skin / 2 (minimum image) since the last rebuild; the decision is taken on the device, so the call
+   sequence is static (CUDA-graph safe).  Neighbours beyond a symmetry function's cutoff contribute exactly zero, so
+   energies and forces agree with skin = 0 up to summation order.  The exact-set queries (pantea_neighbor_counts /
+   _export) and pantea_lj_energy_forces refuse rows built with a skin (PANTEA_EINVAL).  skin = 0 (default) disables. */
+int pantea_workspace_set_skin(pantea_workspace* ws, double skin);
+/* builds[0] = pantea_neighbor_build calls that ran with a skin, builds[1] = how many of them rebuilt the rows
+   (synchronises `stream`) */
+int pantea_neighbor_rebuilds(pantea_workspace* ws, int64_t* builds, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,8 @@ PROTOTYPES = {
     "pantea_bench_fma": (C.c_int, [_I32, _I32, _I32, _I32, _VP, C.POINTER(_DBL), _VP]),
     "pantea_l2_flush": (C.c_int, [_VP, _I64, _VP]),
     "pantea_workspace_set_counters": (C.c_int, [_VP, _VP]),
+    "pantea_workspace_set_skin": (C.c_int, [_VP, _DBL]),
+    "pantea_neighbor_rebuilds": (C.c_int, [_VP, C.POINTER(_I64), _VP]),
 }
 
 _lib: Optional[C.CDLL] = None

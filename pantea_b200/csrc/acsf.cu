@@ -60,7 +60,9 @@ struct AtomArgs {
     const double* boxes;
     BoxArgK box;
     int wrap_jk;
-    double rc_list;  // radius the neighbour rows were built with
+    double rc_list;  // radius the neighbour rows were built with (cutoff + Verlet skin)
+    float skin;      // Verlet skin: the pair lists must stay valid while atoms move by up to skin / 2 each
+    const int32_t* filter_guard;  // skin: the filter is skipped while *filter_guard == 0 (NULL: always run)
     const ElementTable* tables;
     int n_types;
     int element_slot;  // >= 0: apply this element's table to every centre; -1: the atom's own type
@@ -221,6 +223,7 @@ struct FilterSweep {
 template <typename T>
 __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const AtomArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.filter_guard && *a.filter_guard == 0) return;  // rows unchanged since the lists were written
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int w = blockIdx.x * kFilterWarps + wib;
     if (w >= a.n_work) return;
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const At
             const float r2 = fx * fx + fy * fy + fz * fz;
             int bits = 0;
             for (int c = 0; c < n_cls; ++c) {
-                const float rcf = (float)tab.cls[c].rc;
+                const float rcf = (float)tab.cls[c].rc + a.skin;
                 bits |= (r2 < rcf * rcf * 1.0001f + 1e-4f) ? (1 << c) : 0;  // inclusive: exact test in the evaluation
             }
             sf4[n] = make_float4(fx, fy, fz, __int_as_float(bits));
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const At
         const int bj = sg.lo(grp.type_j), nj = sg.hi(grp.type_j) - bj;
         const int bk = sg.lo(grp.type_k), nk = sg.hi(grp.type_k) - bk;
         const bool same = grp.type_j == grp.type_k;
-        const float rcf = (float)tab.cls[grp.cls].rc;
+        const float rcf = (float)tab.cls[grp.cls].rc + a.skin;
         const float rc2f = grp.kind == PANTEA_G3 ? rcf * rcf * 1.0001f + 1e-4f : 3.0e38f;
         // every lane keeps one partner k in registers while the warp sweeps over the neighbours j (broadcast reads).
         // Same-type groups take the unordered pairs j < k: neighbours before the chunk pair with all of its lanes, the
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const At
         const bool swap = !same && nj * ((nk + 31) >> 5) > nk * ((nj + 31) >> 5);
         const int js = swap ? bk : bj, njs = swap ? nk : nj;  // swept bucket
         const int ks = swap ? bj : bk, nks = swap ? nj : nk;  // lane-resident bucket
-        const int variant = (tab.cls[grp.cls].rc < a.rc_list ? 1 : 0) | (wrap_jk ? 2 : 0);
+        const int variant = (tab.cls[grp.cls].rc + (double)a.skin < a.rc_list ? 1 : 0) | (wrap_jk ? 2 : 0);
         for (int k0 = 0; k0 < nks; k0 += 32) {
             const int kk = k0 + lane;
             sw.fk = sf4[ks + (kk < nks ? kk : 0)];
@@ -794,6 +797,8 @@ static int launch_mch(const AtomArgs<T>& a, int max_members, cudaStream_t st) {
     return launch_eval<T, WPA, GRAD, 4>(a, st);
 }
 
+__global__ void skin_lists_fresh_kernel(int32_t* __restrict__ skin_flags) { skin_flags[1] = 0; }
+
 template <typename T>
 static int launch_filter(const AtomArgs<T>& a, cudaStream_t st) {
     const size_t smem = (size_t)kFilterWarps * (a.scap + 1) * sizeof(float4);
@@ -827,6 +832,8 @@ static int ensure_pair_storage(pantea_workspace* ws) {
                     std::string("pair-list allocation: ") + cudaGetErrorString(err));
     ws->pair_cap = want;
     ws->pair_groups = pot->max_groups;
+    ws->lists_valid = false;  // (Verlet skin) fresh storage: the next energy pass filters again
+    ++ws->arg_epoch;
     return PANTEA_OK;
 }
 
@@ -845,6 +852,8 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
     if (ws->box[2] < lmin) lmin = ws->box[2];
     a.wrap_jk = ws->boxes ? 1 : (ws->has_box && 0.5 * lmin < 2.0 * ws->rc * (1.0 + 1e-9) ? 1 : 0);
     a.rc_list = ws->rc;
+    a.skin = ws->skin_active ? (float)ws->skin : 0.f;
+    a.filter_guard = nullptr;
     a.tables = pot->dev; a.n_types = pot->n_elements; a.element_slot = element_slot;
     a.centres = centres;
     const bool energy_pass = (e_atom || forces) && !G && !dG;
@@ -858,6 +867,7 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
         if (!ws->gbuf) {
             const size_t bytes = sizeof(T) * (size_t)ws->max_atoms * (pot->max_sf > 0 ? pot->max_sf : 1) * 4;
             cudaError_t err = cudaMalloc(&ws->gbuf, bytes);
+            ++ws->arg_epoch;
             if (err != cudaSuccess) return fail(PANTEA_ENOMEM, std::string("descriptor hand-off buffer: ") + cudaGetErrorString(err));
         }
         a.gbuf = (T*)ws->gbuf;
@@ -874,8 +884,19 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
         PANTEA_CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     if (pot->max_groups > 0) {
+        // Verlet skin: the energy pass keeps its pair lists until the neighbour rows are rebuilt (device flag)
+        const bool reuse = energy_pass && ws->skin_active;
+        if (reuse) {
+            if (!ws->lists_valid) PANTEA_CUDA_TRY(cudaMemsetAsync(ws->skin_flags + 1, 1, 4, st));
+            a.filter_guard = ws->skin_flags + 1;
+        }
         rc = launch_filter<T>(a, st);
         if (rc != PANTEA_OK) return rc;
+        if (reuse) {
+            skin_lists_fresh_kernel<<<1, 1, 0, st>>>(ws->skin_flags);
+            PANTEA_LAUNCH_CHECK();
+        }
+        ws->lists_valid = reuse;
     }
     const bool grad = dG != nullptr || forces != nullptr;
     const int mm = pot->max_members;

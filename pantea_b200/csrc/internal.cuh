@@ -161,6 +161,21 @@ struct pantea_workspace {
     void* rec = nullptr;           // Rec<T>[max_atoms]
     void* rec_screen = nullptr;    // Rec<float>[max_atoms]: box-wrapped positions for the FP32 screening pass (F64 cell mode)
     int32_t* wide_flag = nullptr;  // [1] set when an atom lies more than a quarter box outside the cell
+    // Verlet skin (pantea_workspace_set_skin)
+    double skin = 0.0;
+    void* pos_ref = nullptr;        // [max_atoms,3] positions at the last rebuild (workspace dtype)
+    int32_t* skin_flags = nullptr;  // device [4]: [0] rebuild in this call, [1] pair lists stale, [2] rebuilds, [3] skin builds
+    bool skin_active = false;       // rows currently hold radius rc + skin and pos_ref matches them
+    bool lists_valid = false;       // pair lists belong to the energy pass over the current rows
+    struct SkinKey {
+        int64_t n = -1, own_begin = 0, own_end = -1;
+        double rc = 0, box[3] = {0, 0, 0};
+        const void* types = nullptr;
+        bool operator==(const SkinKey& o) const {
+            return n == o.n && own_begin == o.own_begin && own_end == o.own_end && rc == o.rc && box[0] == o.box[0] &&
+                   box[1] == o.box[1] && box[2] == o.box[2] && types == o.types;
+        }
+    } skin_key;
     int32_t* slot_of = nullptr;    // [max_atoms] original index -> sorted slot
     int32_t* struct_of = nullptr;  // [max_atoms] structure id per sorted slot (batch mode)
     int32_t* nbr = nullptr;        // [max_atoms * cap] sorted-slot indices, partitioned by bucket
@@ -180,17 +195,18 @@ struct pantea_workspace {
     cudaGraphExec_t md_graph = nullptr;
     cudaStream_t capture_stream = nullptr;
     int md_graph_nodes = 0;        // kernel launches per replay
+    int64_t arg_epoch = 0;         // bumped whenever a buffer / capacity baked into captured kernel arguments changes
     // key of the captured graph
     struct GraphKey {
         const void *pos = nullptr, *vel = nullptr, *frc = nullptr, *mass = nullptr, *types = nullptr, *scalars = nullptr;
-        int64_t n = 0;
+        int64_t n = 0, epoch = -1;
         double dt = 0, tau = 0, t0 = 0, kb = 0, box[3] = {0, 0, 0};
         int record = 0, has_box = 0;
         bool operator==(const GraphKey& o) const {
             return pos == o.pos && vel == o.vel && frc == o.frc && mass == o.mass && types == o.types &&
                    scalars == o.scalars && n == o.n && dt == o.dt && tau == o.tau && t0 == o.t0 && kb == o.kb &&
                    box[0] == o.box[0] && box[1] == o.box[1] && box[2] == o.box[2] && record == o.record &&
-                   has_box == o.has_box;
+                   has_box == o.has_box && epoch == o.epoch;
         }
     } md_key;
 };

@@ -49,6 +49,7 @@ extern "C" int pantea_lj_energy_forces(pantea_workspace* ws, double sigma, doubl
                                        void* e_total, void* stream) {
     if (!ws) return fail(PANTEA_EINVAL, "pantea_lj_energy_forces: NULL workspace");
     if (ws->mode == kModeNone) return fail(PANTEA_EINVAL, "pantea_lj_energy_forces: call pantea_neighbor_build first");
+    if (ws->skin_active) return fail(PANTEA_EINVAL, "pantea_lj_energy_forces: rows were built with a Verlet skin (set skin = 0)");
     if (!e_atom && !forces && !e_total) return fail(PANTEA_EINVAL, "pantea_lj_energy_forces: all outputs are NULL");
     if (ws->n == 0) return PANTEA_OK;
     cudaStream_t st = (cudaStream_t)stream;

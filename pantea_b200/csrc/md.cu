@@ -257,6 +257,7 @@ int pantea_md_run(pantea_workspace* ws, void* positions, void* velocities, void*
         key.scalars = record ? scalars : nullptr; key.n = n_atoms; key.dt = params->dt; key.tau = params->tau;
         key.t0 = params->t_target; key.kb = params->kb; key.record = record ? 1 : 0; key.has_box = box ? 1 : 0;
         for (int k = 0; k < 3; ++k) key.box[k] = box ? box[k] : 0.0;
+        key.epoch = ws->arg_epoch;  // (after the eager step: its lazy allocations are in)
         if (!(ws->md_graph && key == ws->md_key)) {
             if (ws->md_graph) { cudaGraphExecDestroy(ws->md_graph); ws->md_graph = nullptr; }
             cudaGraph_t graph = nullptr;

@@ -57,6 +57,7 @@ int pantea_l2_flush(void* scratch, int64_t bytes, void* stream) {
 // [2] triplet-SF evaluations, accumulated by every subsequent descriptor / energy launch of `ws`.
 int pantea_workspace_set_counters(pantea_workspace* ws, void* counters) {
     if (!ws) return fail(PANTEA_EINVAL, "pantea_workspace_set_counters: NULL workspace");
+    if (ws->counters != (unsigned long long*)counters) ++ws->arg_epoch;
     ws->counters = (unsigned long long*)counters;
     return PANTEA_OK;
 }

@@ -43,7 +43,9 @@ __device__ __forceinline__ int cell_coord(double x, double inv, int n) {
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void cell_assign_kernel(const T* __restrict__ pos, int n, CellArg ca, BoxArg box, int32_t* __restrict__ cell_of,
-                                   int32_t* __restrict__ cell_count, int32_t* __restrict__ wide_flag) {
+                                   int32_t* __restrict__ cell_count, int32_t* __restrict__ wide_flag,
+                                   const int32_t* __restrict__ guard) {
+    if (guard && *guard == 0) return;  // Verlet skin: the rows of the last rebuild are still valid
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     {   // the screening pass measures true minimum-image distances; they equal the reference's single-shift ones only
@@ -63,7 +65,8 @@ __global__ void cell_assign_kernel(const T* __restrict__ pos, int n, CellArg ca,
 
 // exclusive scan of counts[0..n) into start[0..n] by one block; also zeroes `fill`
 __global__ void cell_scan_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ start,
-                                 int32_t* __restrict__ fill) {
+                                 int32_t* __restrict__ fill, const int32_t* __restrict__ guard) {
+    if (guard && *guard == 0) return;
     __shared__ int warp_sums[32];
     __shared__ int carry_s;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthreads = blockDim.x;
@@ -104,7 +107,9 @@ __global__ void cell_scan_kernel(const int32_t* __restrict__ counts, int n, int3
 }
 
 __global__ void cell_scatter_kernel(const int32_t* __restrict__ cell_of, int n, const int32_t* __restrict__ cell_start,
-                                    int32_t* __restrict__ cell_fill, int32_t* __restrict__ tmp_order) {
+                                    int32_t* __restrict__ cell_fill, int32_t* __restrict__ tmp_order,
+                                    const int32_t* __restrict__ guard) {
+    if (guard && *guard == 0) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int c = cell_of[i];
@@ -117,10 +122,13 @@ template <typename T>
 __global__ void cell_sort_pack_kernel(const T* __restrict__ pos, const int32_t* __restrict__ types, int n_types,
                                       const int32_t* __restrict__ cell_start, int ncells,
                                       const int32_t* __restrict__ tmp_order, Rec<T>* __restrict__ rec,
-                                      int32_t* __restrict__ slot_of, Rec<float>* __restrict__ rec_screen, BoxArg box) {
+                                      int32_t* __restrict__ slot_of, Rec<float>* __restrict__ rec_screen, BoxArg box,
+                                      int32_t* __restrict__ cell_fill, const int32_t* __restrict__ guard) {
+    if (guard && *guard == 0) return;
     int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (cell >= ncells) return;
+    if (lane == 0) cell_fill[cell] = 0;  // leave the counting-sort scratch zeroed for the next (device-decided) rebuild
     int lo = cell_start[cell], hi = cell_start[cell + 1];
     for (int a = lo + lane; a < hi; a += 32) {
         int mine = tmp_order[a];
@@ -186,11 +194,13 @@ struct RowArgs {
     const Rec<float>* rec_screen;  // FP32 screening records (F64 cell mode) or NULL
     const int32_t* wide_flag;
     float screen_band;             // |r2_f32 - r2| bound around rc^2 (and around 0)
+    const int32_t* guard;          // Verlet skin: skip the kernel while *guard == 0 (NULL: always run)
 };
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, PANTEA_ROWS_MINBLOCKS) neighbor_rows_kernel(const Rec<T>* __restrict__ rec, RowArgs a) {
     extern __shared__ int32_t smem_rows[];
+    if (a.guard && *a.guard == 0) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int i = blockIdx.x * kWarpsPerBlock + wib;
     if (i >= a.n) return;
@@ -344,6 +354,50 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PANTEA_ROWS_MINBLOCKS) ne
 }
 
 // ------------------------------------------------------------------------------------------------
+// Verlet skin: rebuild decision, record refresh, bookkeeping -- all on the device, so that the launch sequence of a
+// pantea_neighbor_build call does not depend on the outcome (CUDA-graph safe)
+// ------------------------------------------------------------------------------------------------
+// flags[0] = 1 when some atom moved more than skin / 2 (minimum image: the integrator wraps positions) since the rebuild
+template <typename T>
+__global__ void skin_check_kernel(const T* __restrict__ pos, const T* __restrict__ ref, int n, BoxArg box, double limit2,
+                                  int32_t* __restrict__ flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double dx = (double)pos[3 * i] - (double)ref[3 * i], dy = (double)pos[3 * i + 1] - (double)ref[3 * i + 1],
+           dz = (double)pos[3 * i + 2] - (double)ref[3 * i + 2];
+    dx -= box.lx * rint(dx / box.lx); dy -= box.ly * rint(dy / box.ly); dz -= box.lz * rint(dz / box.lz);
+    if (!(dx * dx + dy * dy + dz * dz <= limit2)) flags[0] = 1;  // also catches NaN
+}
+
+// the packed records follow the atoms every call (the slot order of the last rebuild stays)
+template <typename T>
+__global__ void skin_refresh_kernel(const T* __restrict__ pos, Rec<T>* __restrict__ rec, int n) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    Rec<T> r = rec[s];
+    const int i = rec_idx(r);
+    r.x = pos[3 * i]; r.y = pos[3 * i + 1]; r.z = pos[3 * i + 2];
+    rec[s] = r;
+}
+
+template <typename T>
+__global__ void skin_save_kernel(const T* __restrict__ pos, T* __restrict__ ref, int n3, const int32_t* __restrict__ guard) {
+    if (*guard == 0) return;
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n3) ref[e] = pos[e];
+}
+
+__global__ void skin_finish_kernel(int32_t* __restrict__ flags, int32_t* __restrict__ wide_flag) {
+    if (flags[0] != 0) {
+        flags[1] = 1;  // the pair lists of the evaluation are stale
+        flags[2] += 1;
+        *wide_flag = 0;  // consumed by the rows kernel of this rebuild
+    }
+    flags[0] = 0;
+    flags[3] += 1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // export helpers
 // ------------------------------------------------------------------------------------------------
 __global__ void neighbor_counts_kernel(const int32_t* __restrict__ slot_of, const int32_t* __restrict__ tcount, int n,
@@ -420,13 +474,19 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
     BoxArg ba{ws->box[0], ws->box[1], ws->box[2], ws->has_box ? 1 : 0};
     CellArg ca{1, 1, 1, 0, 0, 0};
 
-    bool use_cells = false;
+    bool use_cells = false, use_skin = false;
     if (box && !struct_ptr) {
-        // cell width strictly larger than rc (relative margin covers the rounding of x * inv)
-        const double w = rc * (1.0 + 1e-7);
+        // cell width strictly larger than the list radius (relative margin covers the rounding of x * inv); a Verlet
+        // skin widens the radius when the box still holds three cells per axis, otherwise it is ignored
         int nc[3];
-        for (int k = 0; k < 3; ++k) nc[k] = (int)std::floor(box[k] / w);
-        use_cells = nc[0] >= 3 && nc[1] >= 3 && nc[2] >= 3;
+        for (int pass = ws->skin > 0.0 ? 0 : 1; pass < 2 && !use_cells; ++pass) {
+            const double w = (pass == 0 ? rc + ws->skin : rc) * (1.0 + 1e-7);
+            for (int k = 0; k < 3; ++k) nc[k] = (int)std::floor(box[k] / w);
+            use_cells = nc[0] >= 3 && nc[1] >= 3 && nc[2] >= 3;
+            use_skin = use_cells && pass == 0;
+        }
+        if (use_skin) rc += ws->skin;
+        ws->rc = rc;
         if (use_cells) {
             // keep the cell count bounded for sparse systems / tiny cutoffs: at most ~4 cells per atom
             for (int k = 0; k < 3; ++k) if (nc[k] > 1024) nc[k] = 1024;
@@ -440,23 +500,46 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
             ca = CellArg{nc[0], nc[1], nc[2], nc[0] / box[0], nc[1] / box[1], nc[2] / box[2]};
         }
     }
+    // Verlet skin: decide on the device whether this call rebuilds (first call with these atoms / box / cutoff: always)
+    const int32_t* guard = nullptr;
+    bool forced = false;
+    if (use_skin) {
+        pantea_workspace::SkinKey key;
+        key.n = n; key.own_begin = ws->own_begin; key.own_end = ws->own_end; key.rc = rc; key.types = types;
+        for (int k = 0; k < 3; ++k) key.box[k] = box[k];
+        if (ws->skin_active && key == ws->skin_key) {
+            const double half = 0.5 * ws->skin;
+            skin_check_kernel<T><<<blocks_n, threads, 0, st>>>(pos, (const T*)ws->pos_ref, (int)n, ba, half * half, ws->skin_flags);
+            PANTEA_LAUNCH_CHECK();
+        } else {
+            PANTEA_CUDA_TRY(cudaMemsetAsync(ws->skin_flags, 1, 4, st));  // flags[0] != 0: rebuild
+            ws->lists_valid = false;
+            forced = true;
+        }
+        ws->skin_key = key;
+        guard = ws->skin_flags;
+    }
+    ws->skin_active = use_skin;
+    if (!use_skin) ws->lists_valid = false;
     if (use_cells) {
         const int64_t ncells = (int64_t)ca.nx * ca.ny * ca.nz;
         int rcode = ensure_cell_capacity(ws, ncells);
         if (rcode != PANTEA_OK) return rcode;
         ws->mode = kModeCell;
-        PANTEA_CUDA_TRY(cudaMemsetAsync(ws->cell_fill, 0, 4 * (ncells + 1), st));
-        PANTEA_CUDA_TRY(cudaMemsetAsync(ws->wide_flag, 0, 4, st));
-        cell_assign_kernel<T><<<blocks_n, threads, 0, st>>>(pos, (int)n, ca, ba, ws->cell_of, ws->cell_fill, ws->wide_flag);
+        if (!guard || forced) {  // device-decided rebuilds find the scratch zeroed by the previous rebuild's kernels
+            PANTEA_CUDA_TRY(cudaMemsetAsync(ws->cell_fill, 0, 4 * (ncells + 1), st));
+            PANTEA_CUDA_TRY(cudaMemsetAsync(ws->wide_flag, 0, 4, st));
+        }
+        cell_assign_kernel<T><<<blocks_n, threads, 0, st>>>(pos, (int)n, ca, ba, ws->cell_of, ws->cell_fill, ws->wide_flag, guard);
         PANTEA_LAUNCH_CHECK();
-        cell_scan_kernel<<<1, 1024, 0, st>>>(ws->cell_fill, (int)ncells, ws->cell_start, ws->cell_fill);
+        cell_scan_kernel<<<1, 1024, 0, st>>>(ws->cell_fill, (int)ncells, ws->cell_start, ws->cell_fill, guard);
         PANTEA_LAUNCH_CHECK();
-        cell_scatter_kernel<<<blocks_n, threads, 0, st>>>(ws->cell_of, (int)n, ws->cell_start, ws->cell_fill, ws->tmp_order);
+        cell_scatter_kernel<<<blocks_n, threads, 0, st>>>(ws->cell_of, (int)n, ws->cell_start, ws->cell_fill, ws->tmp_order, guard);
         PANTEA_LAUNCH_CHECK();
         const int blocks_c = (int)((ncells * 32 + threads - 1) / threads);
         cell_sort_pack_kernel<T><<<blocks_c, threads, 0, st>>>(pos, types, ws->n_types, ws->cell_start, (int)ncells,
                                                                ws->tmp_order, rec, ws->slot_of,
-                                                               (Rec<float>*)ws->rec_screen, ba);
+                                                               (Rec<float>*)ws->rec_screen, ba, ws->cell_fill, guard);
         PANTEA_LAUNCH_CHECK();
     } else {
         ws->mode = kModeAllPairs;
@@ -472,6 +555,7 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
     ra.nbr = ws->nbr; ra.tcount = ws->nbr_tcount; ra.flags = ws->flags;
     ra.rec_screen = use_cells ? (const Rec<float>*)ws->rec_screen : nullptr;
     ra.wide_flag = ws->wide_flag;
+    ra.guard = guard;
     {   // error bound of the screening distance (see neighbor_rows_kernel): per-axis |error| <= 5 L 2^-24, squared
         // distance |error| <= 2 sqrt(3) r delta + 3 delta^2 + 4 2^-24 r^2 at r ~ rc; doubled for safety
         const double lmax = std::max(ws->box[0], std::max(ws->box[1], ws->box[2]));
@@ -485,6 +569,14 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
     else
         neighbor_rows_kernel<T, kModeAllPairs><<<blocks_w, kWarpsPerBlock * 32, smem, st>>>(rec, ra);
     PANTEA_LAUNCH_CHECK();
+    if (use_skin) {
+        skin_refresh_kernel<T><<<blocks_n, threads, 0, st>>>(pos, rec, (int)n);
+        PANTEA_LAUNCH_CHECK();
+        skin_save_kernel<T><<<(int)((3 * n + threads - 1) / threads), threads, 0, st>>>(pos, (T*)ws->pos_ref, (int)(3 * n), guard);
+        PANTEA_LAUNCH_CHECK();
+        skin_finish_kernel<<<1, 1, 0, st>>>(ws->skin_flags, ws->wide_flag);
+        PANTEA_LAUNCH_CHECK();
+    }
     return PANTEA_OK;
 }
 
@@ -538,7 +630,11 @@ int pantea_neighbor_status(pantea_workspace* ws, int32_t* max_count, void* strea
         int want = (seen + seen / 10 + 8 + 7) / 8 * 8;
         if (want < 32) want = 32;
         if (want > ws->cap) want = ws->cap;
-        if (want > ws->smem_cap || want < ws->smem_cap - 32) ws->smem_cap = want;
+        if (want > ws->smem_cap || want < ws->smem_cap - 32) {
+            ws->smem_cap = want;
+            ws->lists_valid = false;  // pair lists were cut to the old staged capacity
+            ++ws->arg_epoch;
+        }
     }
     if (h[2] > 0) {  // pair lists: capacity follows the observed maximum (+25 % head-room)
         if (ws->pair_cap > 0 && h[2] > ws->pair_cap) {
@@ -547,7 +643,7 @@ int pantea_neighbor_status(pantea_workspace* ws, int32_t* max_count, void* strea
                   " (re-run: the capacity has been raised)";
         }
         const int want = h[2] + h[2] / 4 + 64;
-        if (want > ws->pair_cap || want < ws->pair_cap / 2) ws->pair_cap_request = want;
+        if (want > ws->pair_cap || want < ws->pair_cap / 2) { ws->pair_cap_request = want; ++ws->arg_epoch; }
     }
     if (code != PANTEA_OK && h[0] <= ws->cap) return fail(code, msg);
     if (h[0] > ws->cap)
@@ -559,6 +655,7 @@ int pantea_neighbor_status(pantea_workspace* ws, int32_t* max_count, void* strea
 int pantea_neighbor_counts(pantea_workspace* ws, int32_t* counts, void* stream) {
     if (!ws || !counts) return fail(PANTEA_EINVAL, "pantea_neighbor_counts: NULL argument");
     if (ws->mode == kModeNone) return fail(PANTEA_EINVAL, "pantea_neighbor_counts: no structure bound");
+    if (ws->skin_active) return fail(PANTEA_EINVAL, "pantea_neighbor_counts: rows were built with a Verlet skin (set skin = 0)");
     if (ws->n == 0) return PANTEA_OK;
     neighbor_counts_kernel<<<(int)((ws->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ws->slot_of, ws->nbr_tcount,
                                                                                        (int)ws->n, counts);
@@ -569,6 +666,7 @@ int pantea_neighbor_counts(pantea_workspace* ws, int32_t* counts, void* stream) 
 int pantea_neighbor_export(pantea_workspace* ws, const int64_t* row_ptr, int32_t* col_idx, void* stream) {
     if (!ws || !row_ptr || !col_idx) return fail(PANTEA_EINVAL, "pantea_neighbor_export: NULL argument");
     if (ws->mode == kModeNone) return fail(PANTEA_EINVAL, "pantea_neighbor_export: no structure bound");
+    if (ws->skin_active) return fail(PANTEA_EINVAL, "pantea_neighbor_export: rows were built with a Verlet skin (set skin = 0)");
     if (ws->n == 0) return PANTEA_OK;
     const int blocks = (int)((ws->n + kWarpsPerBlock - 1) / kWarpsPerBlock);
     const size_t smem = (size_t)kWarpsPerBlock * ws->cap * 4;

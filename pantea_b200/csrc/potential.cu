@@ -216,6 +216,8 @@ int pantea_workspace_create(const pantea_potential* pot, int64_t max_atoms, int3
     alloc(&ws->rec, rsz * max_atoms);
     if (dtype == PANTEA_F64) alloc(&ws->rec_screen, sizeof(Rec<float>) * max_atoms);
     alloc((void**)&ws->wide_flag, 4);
+    alloc(&ws->pos_ref, esz * 3 * max_atoms);
+    alloc((void**)&ws->skin_flags, 4 * 4);
     alloc((void**)&ws->slot_of, 4 * max_atoms);
     alloc((void**)&ws->struct_of, 4 * max_atoms);
     alloc((void**)&ws->nbr, 4 * (size_t)max_atoms * ws->cap);
@@ -229,6 +231,7 @@ int pantea_workspace_create(const pantea_potential* pot, int64_t max_atoms, int3
     alloc(&ws->md_eatom, esz * max_atoms);
     alloc((void**)&ws->md_ke, 8 * 4);
     if (err == cudaSuccess) err = cudaMemset(ws->flags, 0, 16);
+    if (err == cudaSuccess) err = cudaMemset(ws->skin_flags, 0, 16);
     if (err != cudaSuccess) {
         pantea_workspace_destroy(ws);
         return fail(err == cudaErrorMemoryAllocation ? PANTEA_ENOMEM : PANTEA_ECUDA,
@@ -244,16 +247,39 @@ int pantea_workspace_destroy(pantea_workspace* ws) {
     if (ws->capture_stream) cudaStreamDestroy(ws->capture_stream);
     void* ptrs[] = {ws->rec, ws->slot_of, ws->struct_of, ws->nbr, ws->nbr_tcount, ws->cell_of, ws->tmp_order,
                     ws->cell_start, ws->cell_fill, ws->flags, ws->e_partial, ws->md_forces, ws->md_eatom, ws->md_ke,
-                    ws->pairs, ws->pair_off, ws->gbuf, ws->rec_screen, ws->wide_flag};
+                    ws->pairs, ws->pair_off, ws->gbuf, ws->rec_screen, ws->wide_flag, ws->pos_ref, ws->skin_flags};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete ws;
     return PANTEA_OK;
 }
 
+int pantea_workspace_set_skin(pantea_workspace* ws, double skin) {
+    if (!ws) return fail(PANTEA_EINVAL, "pantea_workspace_set_skin: NULL workspace");
+    if (!(skin >= 0.0)) return fail(PANTEA_EINVAL, "pantea_workspace_set_skin: skin must be >= 0");
+    if (skin != ws->skin) {
+        ws->skin = skin;
+        ++ws->arg_epoch;
+        ws->skin_active = false;  // the next build gathers fresh rows
+        ws->lists_valid = false;
+    }
+    return PANTEA_OK;
+}
+
+int pantea_neighbor_rebuilds(pantea_workspace* ws, int64_t* builds, void* stream) {
+    if (!ws || !builds) return fail(PANTEA_EINVAL, "pantea_neighbor_rebuilds: NULL argument");
+    int32_t h[4] = {0, 0, 0, 0};
+    PANTEA_CUDA_TRY(cudaMemcpyAsync(h, ws->skin_flags, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PANTEA_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    builds[0] = h[3];
+    builds[1] = h[2];
+    return PANTEA_OK;
+}
+
 int pantea_workspace_set_owned_range(pantea_workspace* ws, int64_t begin, int64_t end) {
     if (!ws) return fail(PANTEA_EINVAL, "pantea_workspace_set_owned_range: NULL workspace");
     if (end >= 0 && (begin < 0 || begin > end)) return fail(PANTEA_EINVAL, "pantea_workspace_set_owned_range: bad range");
+    if (ws->own_begin != begin || ws->own_end != end) ++ws->arg_epoch;
     ws->own_begin = begin;
     ws->own_end = end;
     return PANTEA_OK;
@@ -271,6 +297,8 @@ int ensure_cell_capacity(pantea_workspace* ws, int64_t ncells) {
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_start, 4 * (ncells + 1)));
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_fill, 4 * (ncells + 1)));
     ws->cell_cap = ncells;
+    ws->skin_active = false;  // fresh (unzeroed) binning scratch: the next build is a forced one
+    ++ws->arg_epoch;
     return PANTEA_OK;
 }
 }  // namespace pantea

@@ -93,7 +93,7 @@ class ReplicatedMD:
 
     def __init__(self, device_potential, positions: torch.Tensor, velocities: torch.Tensor, masses: torch.Tensor,
                  types: torch.Tensor, box: Sequence[float], time_step: float, rank: int = 0, world: int = 1,
-                 thermostat=None, kb: float = 3.166811563e-6) -> None:
+                 thermostat=None, kb: float = 3.166811563e-6, skin: float = 0.0) -> None:
         from pantea_b200 import _lib, engine
 
         self._lib, self.lib = _lib, _lib.load()
@@ -115,6 +115,8 @@ class ReplicatedMD:
         density = n / (self.box[0] * self.box[1] * self.box[2])
         self.ws = engine.Workspace(device_potential, n, engine.estimate_max_neighbors(device_potential.r_cutoff, density, n),
                                    self.dtype)
+        if skin > 0.0:
+            self.ws.set_skin(skin)
         self.lo, self.hi = self.layout.owned()
         self.steps = 0
         self._bind(check=True)

@@ -150,6 +150,7 @@ class Workspace:
         self.dtype = dtype
         self.code = _lib.dtype_code(dtype)
         self.handle = C.c_void_p()
+        self.skin = 0.0
         self._create()
         self.n_atoms = 0
         self._bound: Tuple = ()
@@ -158,6 +159,20 @@ class Workspace:
     def _create(self) -> None:
         pot = self.potential.handle if self.potential is not None else None
         _lib.check(_lib.load().pantea_workspace_create(pot, self.max_atoms, self.max_neighbors, self.code, C.byref(self.handle)))
+        if self.skin > 0.0:
+            _lib.check(_lib.load().pantea_workspace_set_skin(self.handle, float(self.skin)))
+
+    def set_skin(self, skin: float) -> None:
+        """Verlet skin (Bohr) for the energy/force path: neighbour rows and pair lists are reused until an atom has moved
+        more than skin / 2 (decided on the device).  0 disables; exact neighbour-set queries need 0."""
+        self.skin = float(skin)
+        _lib.check(_lib.load().pantea_workspace_set_skin(self.handle, self.skin))
+
+    def rebuild_counts(self) -> Tuple[int, int]:
+        """(neighbour builds that ran with a skin, how many of them rebuilt the rows)."""
+        out = (C.c_int64 * 2)()
+        _lib.check(_lib.load().pantea_neighbor_rebuilds(self.handle, out, _lib.stream_ptr()))
+        return int(out[0]), int(out[1])
 
     def close(self) -> None:
         if self.handle:

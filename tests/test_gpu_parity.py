@@ -364,3 +364,78 @@ def test_md_energy_curve_3000_atoms_matches_oracle(pot):
     assert np.abs(s[:, 0] - sc_o[1:, 0]).max() < 1e-9 * scale
     assert np.abs(e_tot - e_tot_o).max() < 1e-9 * scale          # same drift curve (the reference MD is not conservative)
     assert np.abs(e_tot_o - e_tot_o[0]).max() > 1e-6 * scale     # ... and it does drift: the test is not vacuous
+
+
+# ------------------------------------------------------------------------------------------ Verlet skin
+@pytest.mark.parametrize("use_graph,skin", [(0, 0.6), (1, 0.6), (1, 0.05)])
+def test_md_run_with_verlet_skin_matches_oracle(use_graph, skin, pot):
+    """rows gathered with rc + skin and reused until an atom moved more than skin / 2 (decided on the
+    device).  Neighbours beyond a cutoff contribute exactly zero, so the trajectory equals the oracle's (which rebuilds
+    every step) up to summation order.  skin = 0.05 forces several device-side rebuilds within the run."""
+    import ctypes as C
+    from pantea_b200 import _lib
+    n_atoms, n_steps, dt = 3000, 30, 0.25
+    pos, types, box = water_box(n_atoms)
+    vel, mass = md_velocities(types), water_masses(types)
+    p_o, v_o, f_o, sc_o = c_oracle.md_run(pot, pos, vel, mass, types, box, dt, n_steps, 0.0, 0.0, KB)
+    dev = device_potential_from_specs(pot)
+    ws = _workspace(dev, n_atoms)
+    ws.set_skin(skin)
+    p, v, t, m = cuda(pos), cuda(vel), cuda(types, torch.int32), cuda(mass)
+    ws.bind(p, t, box, dev.r_cutoff)
+    _, _, f = ws.energy_forces(False, True)
+    scal = torch.zeros((n_steps, 2), dtype=torch.float64, device="cuda")
+    params = _lib.MDParams(dt, 0.0, 0.0, KB, 1, use_graph)
+    for _ in range(2):  # a capacity report after the first attempt raises the capacity; the run is then repeated
+        p.copy_(cuda(pos)); v.copy_(cuda(vel))
+        ws.bind(p, t, box, dev.r_cutoff)
+        _, _, f = ws.energy_forces(False, True)
+        b0, r0 = ws.rebuild_counts()
+        _lib.check(_lib.load().pantea_md_run(ws.handle, _lib.ptr(p), _lib.ptr(v), _lib.ptr(f), _lib.ptr(m), _lib.ptr(t),
+                                             n_atoms, _lib.box_arg(box), n_steps, C.byref(params), _lib.ptr(scal),
+                                             _lib.stream_ptr()))
+        code = _lib.load().pantea_neighbor_status(ws.handle, None, _lib.stream_ptr())
+        if code != _lib.PANTEA_ECAPACITY:
+            _lib.check(code)
+            break
+    builds, rebuilds = ws.rebuild_counts()
+    assert builds - b0 == n_steps
+    # the reference integrator carries no mass: atoms cover 0.3 Bohr within ~6 steps, so even the wide skin rebuilds
+    if skin > 0.5:
+        assert 1 <= rebuilds - r0 <= n_steps // 3  # rows reused for several steps at a time
+    else:
+        assert n_steps // 3 < rebuilds - r0 <= n_steps  # rebuilt on demand
+    np.testing.assert_allclose(p.cpu().numpy(), p_o, rtol=0, atol=1e-9)
+    assert rel_err(v.cpu().numpy(), v_o) < 1e-9
+    assert rel_err(f.cpu().numpy(), f_o) < 1e-8
+    np.testing.assert_allclose(scal.cpu().numpy()[:, 0], sc_o[1:, 0], rtol=1e-9, atol=1e-10)
+
+
+def test_verlet_skin_single_evaluations_and_rebuild_trigger(pot):
+    """Energy / forces with a skin equal the oracle's for the bound structure, after small moves (rows reused) and after
+    a move beyond skin / 2 (rows rebuilt); exact-set queries are refused while a skin is active."""
+    n_atoms, skin = 3000, 0.5
+    pos, types, box = water_box(n_atoms)
+    dev = device_potential_from_specs(pot)
+    ws = _workspace(dev, n_atoms)
+    ws.set_skin(skin)
+    t = cuda(types, torch.int32)
+    rng = np.random.default_rng(3)
+    expected_rebuilds = 0
+    for step, amp in enumerate([0.0, 0.05, 0.05, 0.4, 0.02]):
+        pos = np.remainder(pos + amp * rng.uniform(-1, 1, pos.shape) / np.sqrt(3.0), box)
+        p = cuda(pos)
+        ws.bind(p, t, box, dev.r_cutoff)
+        e, _, f = ws.energy_forces(True, True)
+        e_o, _, f_o = c_oracle.energy_forces(pot, pos, types, box)
+        assert abs(float(e) - e_o) <= FP64_TOL * abs(e_o)
+        assert rel_err(f.cpu().numpy(), f_o) < FP64_TOL
+    builds, rebuilds = ws.rebuild_counts()
+    assert builds >= 5 and 2 <= rebuilds < builds  # first build + the 0.4-Bohr move (cumulative drift may add one)
+    with pytest.raises(ValueError):
+        ws.neighbor_lists()
+    ws.set_skin(0.0)
+    ws.bind(cuda(pos), t, box, dev.r_cutoff)
+    row_ptr_o, col_o = c_oracle.neighbors(pos, types, box, dev.r_cutoff)
+    row_ptr, col = ws.neighbor_lists()
+    assert np.array_equal(col.cpu().numpy(), col_o)
