@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--atoms", type=int, default=int(os.environ.get("PANTEA_BENCH_ATOMS", "100000")))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skin", type=float, default=0.0,
+                    help="Verlet skin (Bohr) of the secondary measurement `verlet_skin`; 0 skips it")
     ap.add_argument("--kernel-times", action="store_true",
                     help="after the timed region, print a per-kernel breakdown (CUPTI, diagnostic only) to stderr")
     ap.add_argument("--no-flush", action="store_true", help="diagnostics only: skip the L2 flush between steps")
@@ -219,43 +221,77 @@ def run_b200(args) -> None:
 
     warmup = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps
     warmup = max(warmup, SEGMENT)
-    for attempt in range(6):
-        for _ in range(warmup):
-            md.step()
-        ok = capacity_ok()  # on overflow the library has raised the capacity: run the segment again
-        l0 = lib.pantea_launch_count()
-        md.reset(pos0, vel0)
-        launches_per_reset = lib.pantea_launch_count() - l0
-        if ok:
-            break
-    else:
+    launches_per_reset = 0
+
+    def settle_capacities() -> None:
+        """Untimed: run one full segment until no capacity flag is raised (the library grows its buffers), then reset."""
+        nonlocal launches_per_reset
+        for attempt in range(6):
+            for _ in range(warmup):
+                md.step()
+            ok = capacity_ok()  # on overflow the library has raised the capacity: run the segment again
+            l0 = lib.pantea_launch_count()
+            md.reset(pos0, vel0)
+            launches_per_reset = lib.pantea_launch_count() - l0
+            if ok:
+                return
         raise SystemExit("bench.py: capacities did not settle")
+
+    def timed_steps(k_steps: int):
+        """K steps, each bracketed by CUDA events on the launching stream (L2 flushed before each); returns the summed
+        step time (ms, max over ranks), the wall time and the kernels launched by the steps themselves."""
+        barrier()
+        launches0 = lib.pantea_launch_count()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(k_steps)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(k_steps)]
+        extra_launches = 0
+        wall0 = time.perf_counter()
+        for k in range(k_steps):
+            if k > 0 and k % SEGMENT == 0:
+                md.reset(pos0, vel0)
+                extra_launches += launches_per_reset
+            flush()
+            extra_launches += 0 if args.no_flush else 1
+            starts[k].record()
+            md.step()
+            stops[k].record()
+        barrier()
+        wall_s = time.perf_counter() - wall0
+        n_launch = lib.pantea_launch_count() - launches0 - extra_launches
+        ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+        ms_t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        all_reduce_max(ms_t)
+        return float(ms_t.item()), wall_s, n_launch
+
+    settle_capacities()
     barrier()
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
-    launches0 = lib.pantea_launch_count()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    flush_launches = 0
-    wall0 = time.perf_counter()
-    resets = 0
-    for k in range(args.steps):
-        if k > 0 and k % SEGMENT == 0:
-            md.reset(pos0, vel0)
-            resets += 1
-        flush()
-        flush_launches += 0 if args.no_flush else 1
-        starts[k].record()
-        md.step()
-        stops[k].record()
-    barrier()
-    wall = time.perf_counter() - wall0
-    launches = lib.pantea_launch_count() - launches0 - flush_launches - resets * launches_per_reset  # the K steps' own
-    ms_total = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
-    ms_t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    all_reduce_max(ms_t)
-    ms_total = float(ms_t.item())
+    ms_total, wall, launches = timed_steps(args.steps)
     clocks = sampler.stop() if sampler else None
     value = n * args.steps / (ms_total * 1e-3)
+    if not capacity_ok():
+        raise SystemExit("bench.py: a capacity flag was raised inside the timed region; the measurement is void")
+    max_seen_main = max_seen
+
+    # ---- secondary measurement: the same K steps with Verlet-skin reuse of rows and pair lists ------------------
+    # (the headline above rebuilds the neighbour rows every step, like the reference; this one is reported beside it)
+    skin_info = None
+    if args.skin > 0.0:
+        md.ws.set_skin(args.skin)
+        md.reset(pos0, vel0)
+        settle_capacities()
+        b0, r0 = md.ws.rebuild_counts()
+        ms_skin, _, _ = timed_steps(args.steps)
+        b1, r1 = md.ws.rebuild_counts()
+        if not capacity_ok():
+            raise SystemExit("bench.py: a capacity flag was raised inside the Verlet-skin timed region")
+        skin_info = {"skin_bohr": args.skin, "value": n * args.steps / (ms_skin * 1e-3), "unit": UNIT,
+                     "ms_per_step": ms_skin / args.steps, "neighbor_builds": b1 - b0, "row_rebuilds": r1 - r0,
+                     "what": "same K steps; rows gathered with rc + skin, rebuilt (device-side decision) when an atom "
+                             "moved > skin/2; identical energies/forces up to summation order"}
+        md.ws.set_skin(0.0)
+        md.reset(pos0, vel0)
+        settle_capacities()
 
     if args.kernel_times and rank == 0:  # diagnostic: never feeds a reported number
         from torch.profiler import ProfilerActivity, profile
@@ -269,10 +305,7 @@ def run_b200(args) -> None:
             print(f"[kernel-times] {e.key[:70]:70s} n={e.count:4d} avg={e.device_time_total / e.count / 1e3:8.4f} ms",
                   file=sys.stderr)
 
-    # ---- capacity check after the run (the timed loop never synchronises) ----------------------------
-    if not capacity_ok():
-        raise SystemExit("bench.py: a capacity flag was raised inside the timed region; the measurement is void")
-    mx = C.c_int32(max_seen)
+    mx = C.c_int32(max_seen_main)
 
     # ---- roofline of the dominant kernel (fused atom kernel), rank 0 ---------------------------------
     roofline = None
@@ -390,6 +423,7 @@ def run_b200(args) -> None:
                        "max_neighbors_seen": int(mx.value), "force_mode": "reference (central-role gradient)",
                        "trajectory": f"timed steps replay {SEGMENT}-step segments from the initial state (untimed reset)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "verlet_skin": skin_info,
             "wall_s_timed_region": wall,
         }
         line.update(extra)

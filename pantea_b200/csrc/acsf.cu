@@ -70,6 +70,7 @@ struct AtomArgs {
     int n_work;
     int by_slot;  // 1: work item = cell-sorted slot (energy/force pass); 0: work item = centre list entry
     int own_begin, own_end;
+    const int32_t* owned_slots;  // by_slot passes of a block-owned rank: work item -> slot (NULL: work item = slot)
     // pair lists written by the filter, read by the evaluation
     int32_t* pairs;      // [n_work][pair_cap]  (j | k << 16), row positions within the staged neighbour block
     int32_t* pair_off;   // [n_work][max_groups + 1] offsets of each group's segment
@@ -131,7 +132,7 @@ __device__ __forceinline__ void group_sync(int atom_in_block) {
 template <typename T>
 __device__ __forceinline__ bool resolve_item(const AtomArgs<T>& a, int w, int& slot, int& out_row, int& etype) {
     if (a.by_slot) {
-        slot = w;
+        slot = a.owned_slots ? a.owned_slots[w] : w;
         out_row = rec_idx(a.rec[slot]);
         if (out_row < a.own_begin || out_row >= a.own_end) return false;
     } else {
@@ -858,8 +859,9 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
     a.centres = centres;
     const bool energy_pass = (e_atom || forces) && !G && !dG;
     a.by_slot = energy_pass ? 1 : 0;
-    a.n_work = energy_pass ? (int)ws->n : (int)n_centres;
     a.own_begin = (int)ws->own_begin; a.own_end = ws->own_end < 0 ? (int)ws->n : (int)ws->own_end;
+    a.owned_slots = energy_pass && ws->owned_active ? ws->owned_slots : nullptr;
+    a.n_work = energy_pass ? (a.owned_slots ? a.own_end - a.own_begin : (int)ws->n) : (int)n_centres;
     a.pairs = ws->pairs; a.pair_off = ws->pair_off; a.pair_cap = ws->pair_cap; a.max_groups = pot->max_groups;
     a.G = (T*)G; a.dG = (T*)dG; a.e_atom = (T*)e_atom; a.forces = (T*)forces;
     a.gbuf = nullptr;

@@ -184,6 +184,9 @@ struct pantea_workspace {
     int32_t* tmp_order = nullptr;  // [max_atoms]
     int32_t* cell_start = nullptr; // [cell_cap + 1]
     int32_t* cell_fill = nullptr;  // [cell_cap]
+    int32_t* cell_own = nullptr;   // [cell_cap + 1] owned atoms per cell, then their exclusive scan (block-owned ranks)
+    int32_t* owned_slots = nullptr; // [max_atoms] cell-ordered slots of the owned atoms, ascending
+    bool owned_active = false;     // rows / evaluation run over `owned_slots` (cell mode with a proper owned range)
     int64_t cell_cap = 0;
     int32_t* flags = nullptr;      // [4]: max neighbour count seen, ...
     double* e_partial = nullptr;   // reduction scratch

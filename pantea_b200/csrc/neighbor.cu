@@ -64,8 +64,8 @@ __global__ void cell_assign_kernel(const T* __restrict__ pos, int n, CellArg ca,
 }
 
 // exclusive scan of counts[0..n) into start[0..n] by one block; also zeroes `fill`
-__global__ void cell_scan_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ start,
-                                 int32_t* __restrict__ fill, const int32_t* __restrict__ guard) {
+__global__ void cell_scan_kernel(const int32_t* counts, int n, int32_t* start, int32_t* fill,
+                                 const int32_t* __restrict__ guard) {  // counts may alias start or fill (in place)
     if (guard && *guard == 0) return;
     __shared__ int warp_sums[32];
     __shared__ int carry_s;
@@ -123,13 +123,25 @@ __global__ void cell_sort_pack_kernel(const T* __restrict__ pos, const int32_t* 
                                       const int32_t* __restrict__ cell_start, int ncells,
                                       const int32_t* __restrict__ tmp_order, Rec<T>* __restrict__ rec,
                                       int32_t* __restrict__ slot_of, Rec<float>* __restrict__ rec_screen, BoxArg box,
-                                      int32_t* __restrict__ cell_fill, const int32_t* __restrict__ guard) {
+                                      int32_t* __restrict__ cell_fill, const int32_t* __restrict__ guard,
+                                      int own_begin, int own_end, int32_t* __restrict__ cell_own,
+                                      int32_t* __restrict__ tcount) {
     if (guard && *guard == 0) return;
     int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (cell >= ncells) return;
     if (lane == 0) cell_fill[cell] = 0;  // leave the counting-sort scratch zeroed for the next (device-decided) rebuild
     int lo = cell_start[cell], hi = cell_start[cell + 1];
+    if (cell_own) {  // block-owned ranks: owned atoms of this cell (their slots are compacted by owned_fill_kernel)
+        int owned = 0;
+        for (int a = lo + lane; a < hi; a += 32) {
+            const int idx = tmp_order[a];
+            owned += (idx >= own_begin && idx < own_end) ? 1 : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) owned += __shfl_xor_sync(kFull, owned, o);
+        if (lane == 0) cell_own[cell] = owned;
+    }
     for (int a = lo + lane; a < hi; a += 32) {
         int mine = tmp_order[a];
         int rank = 0;
@@ -139,6 +151,8 @@ __global__ void cell_sort_pack_kernel(const T* __restrict__ pos, const int32_t* 
         rec_set(r, bucket_of(types[mine], n_types), mine);
         rec[lo + rank] = r;
         slot_of[mine] = lo + rank;
+        if (cell_own && !(mine >= own_begin && mine < own_end))  // no row is built for it: report zero neighbours
+            for (int b = 0; b < kBuckets; ++b) tcount[(size_t)(lo + rank) * kBuckets + b] = 0;
         if (rec_screen) {  // box-wrapped coordinates in [0, L], rounded to float
             const double x = (double)r.x, y = (double)r.y, z = (double)r.z;
             Rec<float> f;
@@ -148,6 +162,30 @@ __global__ void cell_sort_pack_kernel(const T* __restrict__ pos, const int32_t* 
             rec_set(f, bucket_of(types[mine], n_types), mine);
             rec_screen[lo + rank] = f;
         }
+    }
+}
+
+// one warp per cell: slots of the cell's owned atoms, in slot order, at own_start[cell] of the compact list
+template <typename T>
+__global__ void owned_fill_kernel(const Rec<T>* __restrict__ rec, const int32_t* __restrict__ cell_start, int ncells,
+                                  const int32_t* __restrict__ own_start, int own_begin, int own_end,
+                                  int32_t* __restrict__ owned_slots, const int32_t* __restrict__ guard) {
+    if (guard && *guard == 0) return;
+    int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (cell >= ncells) return;
+    const int lo = cell_start[cell], hi = cell_start[cell + 1];
+    int out = own_start[cell];
+    for (int s0 = lo; s0 < hi; s0 += 32) {
+        const int s = s0 + lane;
+        bool mine = false;
+        if (s < hi) {
+            const int idx = rec_idx(rec[s]);
+            mine = idx >= own_begin && idx < own_end;
+        }
+        const unsigned m = __ballot_sync(kFull, mine);
+        if (mine) owned_slots[out + __popc(m & ((1u << lane) - 1u))] = s;
+        out += __popc(m);
     }
 }
 
@@ -195,6 +233,8 @@ struct RowArgs {
     const int32_t* wide_flag;
     float screen_band;             // |r2_f32 - r2| bound around rc^2 (and around 0)
     const int32_t* guard;          // Verlet skin: skip the kernel while *guard == 0 (NULL: always run)
+    const int32_t* owned_slots;    // block-owned ranks: the warps walk this compact slot list (NULL: every slot)
+    int n_owned;
 };
 
 template <typename T, int MODE>
@@ -202,8 +242,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PANTEA_ROWS_MINBLOCKS) ne
     extern __shared__ int32_t smem_rows[];
     if (a.guard && *a.guard == 0) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int i = blockIdx.x * kWarpsPerBlock + wib;
-    if (i >= a.n) return;
+    const int w = blockIdx.x * kWarpsPerBlock + wib;
+    if (w >= (a.owned_slots ? a.n_owned : a.n)) return;
+    const int i = a.owned_slots ? a.owned_slots[w] : w;
     int32_t* L = smem_rows + wib * a.cap;
     const Rec<T> ri = rec[i];
     const int oi = rec_idx(ri);
@@ -521,6 +562,9 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
     }
     ws->skin_active = use_skin;
     if (!use_skin) ws->lists_valid = false;
+    const int own_lo = (int)ws->own_begin, own_hi = ws->own_end < 0 ? (int)n : (int)ws->own_end;
+    const bool owned = use_cells && (own_lo > 0 || own_hi < (int)n);
+    ws->owned_active = owned;
     if (use_cells) {
         const int64_t ncells = (int64_t)ca.nx * ca.ny * ca.nz;
         int rcode = ensure_cell_capacity(ws, ncells);
@@ -539,8 +583,16 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
         const int blocks_c = (int)((ncells * 32 + threads - 1) / threads);
         cell_sort_pack_kernel<T><<<blocks_c, threads, 0, st>>>(pos, types, ws->n_types, ws->cell_start, (int)ncells,
                                                                ws->tmp_order, rec, ws->slot_of,
-                                                               (Rec<float>*)ws->rec_screen, ba, ws->cell_fill, guard);
+                                                               (Rec<float>*)ws->rec_screen, ba, ws->cell_fill, guard,
+                                                               own_lo, own_hi, owned ? ws->cell_own : nullptr, ws->nbr_tcount);
         PANTEA_LAUNCH_CHECK();
+        if (owned) {  // compact list of the owned atoms' slots (cell order): scan of the per-cell counts, then fill
+            cell_scan_kernel<<<1, 1024, 0, st>>>(ws->cell_own, (int)ncells, ws->cell_own, ws->cell_fill, guard);
+            PANTEA_LAUNCH_CHECK();
+            owned_fill_kernel<T><<<blocks_c, threads, 0, st>>>(rec, ws->cell_start, (int)ncells, ws->cell_own, own_lo, own_hi,
+                                                               ws->owned_slots, guard);
+            PANTEA_LAUNCH_CHECK();
+        }
     } else {
         ws->mode = kModeAllPairs;
         pack_identity_kernel<T><<<blocks_n, threads, 0, st>>>(pos, types, ws->n_types, (int)n, struct_ptr, (int)n_structs,
@@ -556,13 +608,15 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
     ra.rec_screen = use_cells ? (const Rec<float>*)ws->rec_screen : nullptr;
     ra.wide_flag = ws->wide_flag;
     ra.guard = guard;
+    ra.owned_slots = owned ? ws->owned_slots : nullptr;
+    ra.n_owned = own_hi - own_lo;
     {   // error bound of the screening distance (see neighbor_rows_kernel): per-axis |error| <= 5 L 2^-24, squared
         // distance |error| <= 2 sqrt(3) r delta + 3 delta^2 + 4 2^-24 r^2 at r ~ rc; doubled for safety
         const double lmax = std::max(ws->box[0], std::max(ws->box[1], ws->box[2]));
         const double delta = 5.0 * lmax * 5.9604644775390625e-08;
         ra.screen_band = (float)(2.0 * (3.5 * rc * delta + 3.0 * delta * delta + 3.0e-7 * rc * rc));
     }
-    const int blocks_w = (int)((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const int blocks_w = (int)(((owned ? (int64_t)(own_hi - own_lo) : n) + kWarpsPerBlock - 1) / kWarpsPerBlock);
     const size_t smem = (size_t)kWarpsPerBlock * ws->cap * sizeof(int32_t);
     if (use_cells)
         neighbor_rows_kernel<T, kModeCell><<<blocks_w, kWarpsPerBlock * 32, smem, st>>>(rec, ra);

@@ -224,6 +224,7 @@ int pantea_workspace_create(const pantea_potential* pot, int64_t max_atoms, int3
     alloc((void**)&ws->nbr_tcount, 4 * (size_t)max_atoms * kBuckets);
     alloc((void**)&ws->cell_of, 4 * max_atoms);
     alloc((void**)&ws->tmp_order, 4 * max_atoms);
+    alloc((void**)&ws->owned_slots, 4 * max_atoms);
     alloc((void**)&ws->flags, 4 * 4);
     ws->e_partial_cap = 4096;
     alloc((void**)&ws->e_partial, 8 * ws->e_partial_cap);
@@ -247,7 +248,7 @@ int pantea_workspace_destroy(pantea_workspace* ws) {
     if (ws->capture_stream) cudaStreamDestroy(ws->capture_stream);
     void* ptrs[] = {ws->rec, ws->slot_of, ws->struct_of, ws->nbr, ws->nbr_tcount, ws->cell_of, ws->tmp_order,
                     ws->cell_start, ws->cell_fill, ws->flags, ws->e_partial, ws->md_forces, ws->md_eatom, ws->md_ke,
-                    ws->pairs, ws->pair_off, ws->gbuf, ws->rec_screen, ws->wide_flag, ws->pos_ref, ws->skin_flags};
+                    ws->pairs, ws->pair_off, ws->gbuf, ws->rec_screen, ws->wide_flag, ws->pos_ref, ws->skin_flags, ws->owned_slots, ws->cell_own};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete ws;
@@ -292,10 +293,12 @@ int ensure_cell_capacity(pantea_workspace* ws, int64_t ncells) {
     if (ncells <= ws->cell_cap) return PANTEA_OK;
     if (ws->cell_start) cudaFree(ws->cell_start);
     if (ws->cell_fill) cudaFree(ws->cell_fill);
-    ws->cell_start = ws->cell_fill = nullptr;
+    if (ws->cell_own) cudaFree(ws->cell_own);
+    ws->cell_start = ws->cell_fill = ws->cell_own = nullptr;
     ws->cell_cap = 0;
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_start, 4 * (ncells + 1)));
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_fill, 4 * (ncells + 1)));
+    PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_own, 4 * (ncells + 1)));
     ws->cell_cap = ncells;
     ws->skin_active = false;  // fresh (unzeroed) binning scratch: the next build is a forced one
     ++ws->arg_epoch;
