@@ -902,8 +902,10 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
     }
     const bool grad = dG != nullptr || forces != nullptr;
     const int mm = pot->max_members;
-    // few atoms: several warps per atom so that every SM sub-partition has work
-    const bool wide = (int64_t)a.n_work < (int64_t)g_num_sms * 64;
+    // few atoms: several warps per atom so that every SM sub-partition has work.  The energy pass decides on the
+    // system size, not on this rank's share: the summation order -- hence every bit of the result -- is then the same
+    // on 1 and on N GPUs
+    const bool wide = (int64_t)(energy_pass ? (int)ws->n : a.n_work) < (int64_t)g_num_sms * 64;
     if (wide) rc = grad ? launch_mch<T, 4, true>(a, mm, st) : launch_mch<T, 4, false>(a, mm, st);
     else rc = grad ? launch_mch<T, PANTEA_EVAL_WPA, true>(a, mm, st) : launch_mch<T, PANTEA_EVAL_WPA, false>(a, mm, st);
     if (rc != PANTEA_OK || !a.gbuf) return rc;

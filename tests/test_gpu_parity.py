@@ -276,16 +276,20 @@ def test_results_are_bitwise_reproducible(pot):
     assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
 
 
-def test_owned_range_partition_matches_full(pot):
-    """Multi-GPU ownership: evaluating the atoms in two index blocks gives the same per-atom results."""
-    pos, types, box = water_box(3000)
+@pytest.mark.parametrize("n_atoms,blocks", [(3000, ((0, 1700), (1700, 3000))),
+                                            (12000, ((0, 1500), (1500, 7000), (7000, 12000)))])
+def test_owned_range_partition_matches_full(n_atoms, blocks, pot):
+    """Multi-GPU ownership: evaluating the atoms in index blocks gives bitwise the same per-atom results as one pass
+    over all atoms (12 000 atoms: the blocks fall below the size where a lone system would switch to several warps per
+    atom -- the choice must follow the system, not the share)."""
+    pos, types, box = water_box(n_atoms)
     dev = device_potential_from_specs(pot)
-    ws = _workspace(dev, 3000)
+    ws = _workspace(dev, n_atoms)
     p, t = cuda(pos), cuda(types, torch.int32)
     ws.bind(p, t, box, dev.r_cutoff)
     _, ea_full, f_full = ws.energy_forces(True, True, True)
     ea, f = torch.zeros_like(ea_full), torch.zeros_like(f_full)
-    for lo, hi in ((0, 1700), (1700, 3000)):
+    for lo, hi in blocks:
         ws.bind(p, t, box, dev.r_cutoff, owned=(lo, hi))
         e_part, ea_part, f_part = ws.energy_forces(True, True, True)
         ea[lo:hi], f[lo:hi] = ea_part[lo:hi], f_part[lo:hi]
