@@ -222,6 +222,14 @@ int pantea_workspace_set_skin(pantea_workspace* ws, double skin);
    (synchronises `stream`) */
 int pantea_neighbor_rebuilds(pantea_workspace* ws, int64_t* builds, void* stream);
 
+/* Per-feature statistics of a descriptor batch: data is a row-major DEVICE matrix [n_rows, n_cols] (row stride `ld`
+   elements, PANTEA_F32 / PANTEA_F64); stats is DEVICE double[4 * n_cols] = mean | population sigma (two-pass) | min |
+   max.  Replaces the jnp.mean / jnp.std / jnp.min / jnp.max reductions of DescriptorScaler.fit / partial_fit
+   (descriptors/scaler.py:250-283), i.e. the work of trainer.fit_scaler (potentials/nnp/trainer.py:68-88).  Fixed-shape
+   two-stage reductions: bitwise reproducible. */
+int pantea_scaler_stats(const void* data, int64_t n_rows, int64_t n_cols, int64_t ld, int32_t dtype, double* stats,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

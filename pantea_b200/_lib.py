@@ -79,6 +79,7 @@ PROTOTYPES = {
     "pantea_workspace_set_counters": (C.c_int, [_VP, _VP]),
     "pantea_workspace_set_skin": (C.c_int, [_VP, _DBL]),
     "pantea_neighbor_rebuilds": (C.c_int, [_VP, C.POINTER(_I64), _VP]),
+    "pantea_scaler_stats": (C.c_int, [_VP, _I64, _I64, _I64, _I32, _VP, _VP]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -84,10 +84,25 @@ class DescriptorScaler:
     # ---------------------------------------------------------------- fitting (scaler.py:249-283)
     @classmethod
     def fit(cls, data: Array) -> ScalerParams:
+        """Per-feature mean / sigma / min / max of a descriptor batch (`scaler.py:250-259`).  Device-resident batches
+        go through the library's two-pass reduction (`pantea_scaler_stats`); host tensors (unit tests of the host
+        logic, tiny inputs) use the same definitions in torch."""
         data = torch.atleast_2d(data)
+        dimension = asarray(data.shape[1], dtype=default_dtype.INT)
+        nsamples = asarray(data.shape[0], dtype=default_dtype.INT)
+        if data.is_cuda and data.dtype in (torch.float32, torch.float64) and data.numel() > 0:
+            from pantea_b200 import _lib
+            data = data if data.stride(1) == 1 else data.contiguous()
+            n, d = data.shape
+            stats = torch.empty((4, d), dtype=torch.float64, device=data.device)
+            import ctypes
+            _lib.check(_lib.load().pantea_scaler_stats(ctypes.c_void_p(data.data_ptr()), n, d, data.stride(0), _lib.dtype_code(data.dtype),
+                                                       _lib.ptr(stats), _lib.stream_ptr()))
+            stats = stats.to(data.dtype)
+            return ScalerParams(dimension, nsamples, stats[0], stats[1], stats[2], stats[3])
         return ScalerParams(
-            dimension=asarray(data.shape[1], dtype=default_dtype.INT),
-            nsamples=asarray(data.shape[0], dtype=default_dtype.INT),
+            dimension=dimension,
+            nsamples=nsamples,
             mean=data.mean(dim=0),
             sigma=data.std(dim=0, unbiased=False),
             minval=data.min(dim=0).values,
@@ -95,17 +110,25 @@ class DescriptorScaler:
         )
 
     @classmethod
-    def partial_fit(cls, params: ScalerParams, data: Array) -> ScalerParams:
-        data = torch.atleast_2d(data)
-        new = cls.fit(data)
-        m, n = params.nsamples.to(data.dtype), data.shape[0]  # fractions in the data precision, not torch's float32 default
+    def merge(cls, params: ScalerParams, new: ScalerParams) -> ScalerParams:
+        """Statistics of the union of two batches from their separate statistics: the combination rule of
+        `_partial_fit` (`scaler.py:262-283`), coefficients split exactly as there."""
+        dtype = params.mean.dtype
+        m, n = params.nsamples.to(dtype), new.nsamples.to(dtype)  # fractions in the data precision
         fm, fn = m / (m + n), n / (m + n)
         diff = params.mean - new.mean
         mean = fm * params.mean + fn * new.mean
         sigma = torch.sqrt((fm * params.sigma) * params.sigma + (fn * new.sigma) * new.sigma
                            + (fm * diff) * (fn * diff))
-        return ScalerParams(params.dimension, params.nsamples + n, mean, sigma,
+        return ScalerParams(params.dimension, params.nsamples + new.nsamples.to(params.nsamples.dtype), mean, sigma,
                             torch.minimum(params.minval, new.minval), torch.maximum(params.maxval, new.maxval))
+
+    @classmethod
+    def partial_fit(cls, params: ScalerParams, data: Array) -> ScalerParams:
+        data = torch.atleast_2d(data)
+        new = cls.fit(data)
+        new = ScalerParams(new.dimension, new.nsamples.to(params.mean.device), *(t.to(params.mean.device) for t in new[2:]))
+        return cls.merge(params, new)
 
     @classmethod
     def initialize_warnings(cls, number_of_warnings: int = 0, max_number_of_warnings: int = -1) -> ScalerWarnings:

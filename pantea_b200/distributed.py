@@ -88,6 +88,47 @@ def all_reduce_max(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def merge_scaler_params(params):
+    """Combine every rank's scaler statistics into the statistics of the whole dataset (the cross-GPU step of
+    SURVEY 8(e) "dataset preprocessing": structures are split across ranks, then `[count, mean, sigma, min, max]` are
+    exchanged).  One all-gather of 1 + 4 d numbers; every rank folds the W contributions in rank order with the
+    reference's own combination rule (`scaler.py:262-283`), so all ranks end with bitwise the same result.  A rank
+    that saw no sample of the element passes `None`."""
+    from pantea_b200.descriptors.scaler import DescriptorScaler, ScalerParams
+
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return params
+    world = dist.get_world_size()
+    # the feature count is a property of the potential; ranks without data learn it from the others
+    d_local = int(params.dimension) if params is not None else 0
+    dev = params.mean.device if params is not None else torch.device("cuda" if dist.get_backend() == "nccl" else "cpu")
+    d_t = torch.tensor([d_local], dtype=torch.int64, device=dev)
+    dist.all_reduce(d_t, op=dist.ReduceOp.MAX)
+    d = int(d_t.item())
+    if d == 0:
+        return None
+    dtype = params.mean.dtype if params is not None else torch.float64
+    dt_code = torch.tensor([0 if dtype == torch.float64 else 1], dtype=torch.int64, device=dev)
+    dist.all_reduce(dt_code, op=dist.ReduceOp.MAX)
+    dtype64 = torch.float64
+    packed = torch.zeros(1 + 4 * d, dtype=dtype64, device=dev)
+    if params is not None:
+        packed[0] = float(params.nsamples)
+        packed[1:] = torch.cat([params.mean, params.sigma, params.minval, params.maxval]).to(dtype64)
+    gathered = [torch.empty_like(packed) for _ in range(world)]
+    dist.all_gather(gathered, packed)
+    out = None
+    out_dtype = torch.float64 if int(dt_code.item()) == 0 else torch.float32
+    for g in gathered:
+        n = int(round(float(g[0])))
+        if n == 0:
+            continue
+        mean, sigma, mn, mx = (g[1 + k * d: 1 + (k + 1) * d].to(out_dtype) for k in range(4))
+        cur = ScalerParams(torch.tensor(d, dtype=torch.int32), torch.tensor(n, dtype=torch.int32), mean, sigma, mn, mx)
+        out = cur if out is None else DescriptorScaler.merge(out, cur)
+    return out
+
+
 class ReplicatedMD:
     """Velocity-Verlet MD of one periodic box on `world` GPUs (reference integrator, no mass)."""
 

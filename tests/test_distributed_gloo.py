@@ -57,3 +57,42 @@ def test_block_layout_properties():
             covered += list(range(lo, hi))
         assert covered == list(range(n))
         assert BlockLayout(n, 0, w).padded % w == 0 and BlockLayout(n, 0, w).padded >= n
+
+
+def _scaler_worker(rank, world, port, out):
+    from pantea_b200.descriptors.scaler import DescriptorScaler
+    from pantea_b200.distributed import merge_scaler_params
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        data = torch.from_numpy(np.random.default_rng(42).normal(2.0, 3.0, size=(37, 5)))
+        mine = data[rank::world]                       # structures are split index mod world
+        params = DescriptorScaler.fit(mine[:3])
+        params = DescriptorScaler.partial_fit(params, mine[3:])
+        merged = merge_scaler_params(params)
+        empty = merge_scaler_params(params if rank == 0 else None)   # a rank without samples of the element
+        out[rank] = (merged.nsamples.item(), merged.mean.numpy(), merged.sigma.numpy(), merged.minval.numpy(),
+                     merged.maxval.numpy(), empty.nsamples.item(), empty.mean.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_scaler_statistics_merge_across_ranks_world2():
+    """SURVEY 8(e) dataset preprocessing: per-rank scaler statistics merged into the whole-dataset ones."""
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_scaler_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        res = dict(out)
+    data = np.random.default_rng(42).normal(2.0, 3.0, size=(37, 5))
+    for r in range(world):
+        n, mean, sigma, mn, mx, n_e, mean_e = res[r]
+        assert n == 37
+        np.testing.assert_allclose(mean, data.mean(0), rtol=1e-13)
+        np.testing.assert_allclose(sigma, data.std(0), rtol=1e-12)
+        np.testing.assert_array_equal(mn, data.min(0))
+        np.testing.assert_array_equal(mx, data.max(0))
+        assert n_e == len(data[0::2])
+        np.testing.assert_allclose(mean_e, data[0::2].mean(0), rtol=1e-13)
+    for k in range(1, 5):
+        np.testing.assert_array_equal(res[0][k], res[1][k])        # every rank holds bitwise the same statistics

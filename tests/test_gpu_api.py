@@ -263,3 +263,72 @@ def test_reference_md_lj_attributes(vec):
     assert md.step == 1 and md.elapsed_time == pytest.approx(dt)
     np.testing.assert_allclose(_np(system.get_center_of_mass_velocity()), 0.0, atol=1e-10)
     np.testing.assert_allclose(_np(system.get_center_of_mass_position()), v["com_position"], rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ scaler fitting (8(f)-2)
+@pytest.mark.parametrize("dtype,n_rows,n_cols", [(torch.float64, 1, 3), (torch.float64, 777, 27), (torch.float64, 20011, 70),
+                                                 (torch.float32, 5000, 33)])
+def test_scaler_statistics_kernel_matches_definitions(dtype, n_rows, n_cols):
+    """pantea_scaler_stats (two-pass mean / population sigma / min / max per feature) against numpy float64, through
+    DescriptorScaler.fit on a device-resident batch; also a strided (non-contiguous rows) view."""
+    from pantea_b200.descriptors import DescriptorScaler
+    rng = np.random.default_rng(9)
+    host = (rng.normal(1.5, 2.0, size=(n_rows, n_cols + 5)) * rng.uniform(1e-3, 1e3, size=n_cols + 5)).astype(
+        np.float64 if dtype == torch.float64 else np.float32)
+    dev = torch.as_tensor(host, device="cuda")
+    tol = 1e-12 if dtype == torch.float64 else 2e-6
+    for view, ref in ((dev[:, :n_cols], host[:, :n_cols].astype(np.float64)), (dev.contiguous(), host.astype(np.float64))):
+        p = DescriptorScaler.fit(view)
+        assert int(p.nsamples) == n_rows and int(p.dimension) == view.shape[1] and p.mean.dtype == dtype
+        scale = np.abs(ref).max(0)  # per feature: the columns span six orders of magnitude
+        assert (np.abs(_np(p.mean) - ref.mean(0)) <= tol * scale).all()
+        assert (np.abs(_np(p.sigma) - ref.std(0)) <= max(tol, 1e-11) * scale).all()
+        np.testing.assert_array_equal(_np(p.minval).astype(np.float64), ref.min(0))
+        np.testing.assert_array_equal(_np(p.maxval).astype(np.float64), ref.max(0))
+    again = DescriptorScaler.fit(dev[:, :n_cols])
+    assert torch.equal(again.sigma, DescriptorScaler.fit(dev[:, :n_cols]).sigma)  # fixed-order reduction
+
+
+def test_fit_scaler_over_a_dataset_matches_oracle_descriptors(golden_dir):
+    """trainer.fit_scaler (reference trainer.py:68-88): statistics of the ACSF descriptors of every element over a
+    dataset of water boxes, against numpy statistics of the oracle's descriptors of the same structures; a 2-way split
+    of the dataset merged with the reference's partial_fit rule gives the same numbers."""
+    from oracle import c_oracle
+    from oracle.spec import load_potential, water_box
+    from pantea_b200.atoms import Structure
+    from pantea_b200.descriptors import DescriptorScaler
+    from pantea_b200.potentials import NeuralNetworkPotential
+    from pantea_b200.potentials.nnp import NeuralNetworkPotentialTrainer
+    specs = {s.atom_type: s for s in load_potential(golden_dir / "h2o.json")}
+    names = {1: "H", 2: "O"}
+    structures, expected = [], {"H": [], "O": []}
+    for seed, n_atoms in ((1, 192), (2, 192), (3, 81), (4, 648)):
+        pos, types, box = water_box(n_atoms, seed=seed)
+        structures.append(Structure.from_dict({"elements": [names[int(t)] for t in types], "positions": pos,
+                                               "lattice": np.diag(box)}, dtype=torch.float64))
+        for t, name in names.items():
+            G, _ = c_oracle.acsf(specs[t], pos, types, box, centres=np.nonzero(types == t)[0], grad=False)
+            expected[name].append(G)
+    nnp = NeuralNetworkPotential.from_runner(golden_dir / "h2o.json")
+    params = NeuralNetworkPotentialTrainer(nnp).fit_scaler(structures)
+    for name in ("H", "O"):
+        ref = np.concatenate(expected[name])
+        p = params[name]
+        assert int(p.nsamples) == len(ref) and int(p.dimension) == ref.shape[1]
+        np.testing.assert_allclose(_np(p.mean), ref.mean(0), rtol=1e-10)
+        np.testing.assert_allclose(_np(p.sigma), ref.std(0), rtol=1e-9)
+        np.testing.assert_allclose(_np(p.minval), ref.min(0), rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(_np(p.maxval), ref.max(0), rtol=1e-10)
+    # the same dataset in two shards (what two ranks would hold), merged
+    shards = []
+    for r in range(2):
+        part = NeuralNetworkPotential.from_runner(golden_dir / "h2o.json")
+        shards.append(NeuralNetworkPotentialTrainer(part).fit_scaler(structures[r::2]))
+    for name in ("H", "O"):
+        merged = DescriptorScaler.merge(shards[0][name], shards[1][name])
+        np.testing.assert_allclose(_np(merged.mean), _np(params[name].mean), rtol=1e-12)
+        np.testing.assert_allclose(_np(merged.sigma), _np(params[name].sigma), rtol=1e-10)
+        assert int(merged.nsamples) == int(params[name].nsamples)
+    # fitted parameters are usable: the potential evaluates with them once model weights are loaded
+    nnp.load_model()
+    assert torch.isfinite(nnp(structures[0]))
