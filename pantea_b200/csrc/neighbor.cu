@@ -684,7 +684,9 @@ int pantea_neighbor_status(pantea_workspace* ws, int32_t* max_count, void* strea
         int want = (seen + seen / 10 + 8 + 7) / 8 * 8;
         if (want < 32) want = 32;
         if (want > ws->cap) want = ws->cap;
-        if (want > ws->smem_cap || want < ws->smem_cap - 32) {
+        // sized from the first observation, afterwards it only grows: shrinking on a later, smaller observation would
+        // oscillate when the same trajectory (e.g. a densifying box) is run again after a capacity report
+        if (ws->smem_cap == 0 || want > ws->smem_cap) {
             ws->smem_cap = want;
             ws->lists_valid = false;  // pair lists were cut to the old staged capacity
             ++ws->arg_epoch;
@@ -697,7 +699,8 @@ int pantea_neighbor_status(pantea_workspace* ws, int32_t* max_count, void* strea
                   " (re-run: the capacity has been raised)";
         }
         const int want = h[2] + h[2] / 4 + 64;
-        if (want > ws->pair_cap || want < ws->pair_cap / 2) { ws->pair_cap_request = want; ++ws->arg_epoch; }
+        // grow whenever needed; shrink only once, when the first observation shows the initial guess to be far too large
+        if (want > ws->pair_cap || (ws->pair_cap_request == 0 && want < ws->pair_cap / 2)) { ws->pair_cap_request = want; ++ws->arg_epoch; }
     }
     if (code != PANTEA_OK && h[0] <= ws->cap) return fail(code, msg);
     if (h[0] > ws->cap)
