@@ -44,6 +44,19 @@ def test_error_convention_without_gpu():
     assert lib.pantea_workspace_create(None, 64, 32, 16, ctypes.byref(handle)) == _lib.PANTEA_EINVAL
     with pytest.raises(ValueError):
         _lib.check(lib.pantea_workspace_set_owned_range(None, 0, 1))
+    # argument validation of the later entry points happens before any CUDA call
+    counts = (ctypes.c_int64 * 2)()
+    stats = ctypes.c_void_p(16)  # never dereferenced: the checks below fail first
+    for call, needle in (
+            (lambda: lib.pantea_workspace_set_skin(None, 0.5), b"NULL workspace"),
+            (lambda: lib.pantea_neighbor_rebuilds(None, counts, None), b"NULL argument"),
+            (lambda: lib.pantea_scaler_stats(None, 4, 3, 3, 64, stats, None), b"NULL argument"),
+            (lambda: lib.pantea_scaler_stats(stats, 0, 3, 3, 64, stats, None), b"n_rows >= 1"),
+            (lambda: lib.pantea_scaler_stats(stats, 4, 3, 2, 64, stats, None), b"n_cols <= ld"),
+            (lambda: lib.pantea_lj_energy_forces(None, 1.0, 1.0, None, None, None, None), b"NULL workspace"),
+            (lambda: lib.pantea_neighbor_build(None, None, None, 0, None, 1.0, None), b"NULL argument")):
+        code = call()
+        assert code == _lib.PANTEA_EINVAL and needle in lib.pantea_last_error(), (code, lib.pantea_last_error())
 
 
 def test_product_package_never_imports_the_oracle():
