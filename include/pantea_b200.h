@@ -62,6 +62,9 @@ enum { PANTEA_ACT_IDENTITY = 0, PANTEA_ACT_TANH = 1, PANTEA_ACT_LOGISTIC = 2, PA
 
 /* force definitions */
 #define PANTEA_FORCE_REFERENCE 0 /* -dE_i/dr_i in the central role only == reference force.py:16-43 */
+#define PANTEA_FORCE_FULL 1      /* -dE/dr_i of the total energy: every centre's contributions are also scattered to
+                                    its neighbours (Newton's third law holds).  Not a reference mode: the reference
+                                    differentiates the central copy of the positions only. */
 
 typedef struct pantea_symfunc_desc {
     int32_t kind;        /* PANTEA_G1 / G2 / G3 / G9 */
@@ -156,7 +159,12 @@ int pantea_acsf_compute(pantea_workspace* ws, int32_t element, const int32_t* ce
       (reference energy.py:45-66, force.py:16-43, potential.py:67-102).  One fused launch per call:
       symmetry functions + central gradients -> scaler -> per-element network forward/backward ->
       F_i = -sum_s dE_i/dG_is dG_is/dr_i.  e_atom [n] / forces [n,3] / e_total [1] may each be NULL.
-      Only the owned range is written; e_total sums the owned atoms (deterministic order). */
+      Only the owned range is written; e_total sums the owned atoms (deterministic order).
+      force_mode PANTEA_FORCE_FULL: symmetry-function values -> networks -> a second pass over the same pair lists that
+      scatters dE_i/dG_is dG_is/d(r_i - r_j) to the centre AND to its neighbours (shared-memory accumulation per neighbour,
+      then one global atomic per neighbour and component; summation order, hence the last bits, not reproducible).
+      All n rows of `forces` are zeroed and written: rows outside the owned range receive the owned centres' contributions
+      to them (a multi-GPU caller sums those back onto their owners: pantea_halo_unpack_add). */
 int pantea_energy_forces(pantea_workspace* ws, void* e_atom, void* forces, void* e_total, int32_t force_mode,
                          void* stream);
 
@@ -229,6 +237,20 @@ int pantea_neighbor_rebuilds(pantea_workspace* ws, int64_t* builds, void* stream
    two-stage reductions: bitwise reproducible. */
 int pantea_scaler_stats(const void* data, int64_t n_rows, int64_t n_cols, int64_t ld, int32_t dtype, double* stats,
                         void* stream);
+
+/* -- halo exchange of the brick-decomposed MD; the transport itself is NCCL send/recv issued by the
+      caller (torch.distributed all_to_all_single), these are the device-side pack / unpack steps.
+   pantea_halo_pack: send_buf[i] = positions[send_idx[i]] for the fixed send list of the current ghost shell, and -- when
+      pos_ref is given -- raise the sticky DEVICE flag *violated if an owned atom [0,n_own) moved more than `limit`
+      (= skin / 2; nearest image in the HOST box, NULL = open) away from pos_ref, the positions the lists were built on.
+   pantea_halo_unpack_add: out[a] += sum of recv_buf[e] over the entries e of the send list that refer to owned atom a
+      (reverse halo of PANTEA_FORCE_FULL); order [n_send] = send-list entries sorted by atom (stable), first [n_own+1] =
+      each atom's range in `order`.  One thread per atom, fixed order: reproducible. */
+int pantea_halo_pack(const void* positions /*[n,3]*/, const int64_t* send_idx, int64_t n_send, void* send_buf /*[n_send,3]*/,
+                     const void* pos_ref /*[n_own,3] or NULL*/, int64_t n_own, const double* box, double limit,
+                     int32_t* violated, int32_t dtype, void* stream);
+int pantea_halo_unpack_add(void* out /*[n_own,3]*/, const void* recv_buf /*[n_send,3]*/, const int64_t* order,
+                           const int64_t* first, int64_t n_own, int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -275,6 +275,25 @@ def energy_and_forces(models: Sequence[ElementModel], positions: Tensor, types: 
     return e_atom.sum(), e_atom, forces
 
 
+def energy_and_full_forces(models: Sequence[ElementModel], positions: Tensor, types: Tensor, box: Optional[Tensor],
+                           chunk: int = 16) -> Tuple[Tensor, Tensor]:
+    """Total energy and F = -dE/dr with respect to ALL occurrences of the positions (centre and neighbour roles).
+
+    NOT a reference mode: the reference differentiates the central copy only (force.py:16-43, see
+    `energy_and_forces`).  This is the oracle of the library's PANTEA_FORCE_FULL extension:
+    the same energy expression as above, plain reverse-mode autograd through both roles.
+    """
+    pos = positions.detach().clone().requires_grad_(True)
+    total = pos.new_zeros(())
+    for model in models:
+        idx_all = torch.nonzero(types == model.atom_type, as_tuple=True)[0]
+        for s in range(0, len(idx_all), chunk):
+            idx = idx_all[s:s + chunk]
+            total = total + model.energies(pos[idx], pos, types, box).sum()
+    (g,) = torch.autograd.grad(total, pos)
+    return total.detach(), -g
+
+
 # ----------------------------------------------------------------------------- MD pieces
 def verlet_positions(x: Tensor, v: Tensor, f: Tensor, dt: float) -> Tensor:
     """pantea/simulation/molecular_dynamics.py:16-21 (no mass division)."""

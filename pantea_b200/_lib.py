@@ -17,6 +17,7 @@ LIB_PATH = _PKG / "libpantea_b200.so"
 
 PANTEA_OK, PANTEA_EINVAL, PANTEA_ECUDA, PANTEA_ECAPACITY, PANTEA_ENOMEM = 0, -1, -2, -3, -4
 PANTEA_F64, PANTEA_F32 = 64, 32
+FORCE_REFERENCE, FORCE_FULL = 0, 1
 MAX_TYPES, MAX_SYMFUNC, MAX_LAYERS, MAX_CUTOFFS = 8, 128, 8, 4
 
 
@@ -80,6 +81,8 @@ PROTOTYPES = {
     "pantea_workspace_set_skin": (C.c_int, [_VP, _DBL]),
     "pantea_neighbor_rebuilds": (C.c_int, [_VP, C.POINTER(_I64), _VP]),
     "pantea_scaler_stats": (C.c_int, [_VP, _I64, _I64, _I64, _I32, _VP, _VP]),
+    "pantea_halo_pack": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _I64, C.POINTER(_DBL), _DBL, _VP, _I32, _VP]),
+    "pantea_halo_unpack_add": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _VP]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -81,6 +81,7 @@ struct AtomArgs {
     T* e_atom;
     T* forces;
     T* gbuf;  // [n_work][n_sf_max][4] summed descriptors handed from the evaluation to the network kernel
+    T* wbuf;  // full-force mode: [n_work][n_sf_max] dE_i/dG_is written by the network kernel, read by the scatter pass
     unsigned long long* counters;  // optional work counters: [0] pairs, [1] radial-SF evals, [2] triplet-SF evals
     int n_cls_max, n_sf_max, n_neurons_max, width_max;
 };
@@ -693,7 +694,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_force_kernel(const AtomArgs<T
             in_off = out_off; out_off += no;
         }
         energy = sh[in_off * kMlpThreads];
-        if (a.forces) {
+        if (a.forces || a.wbuf) {
             gc[0] = (T)1;
             int lay_out = out_off - tab.sizes[L];  // offset (in sh) of the outputs of layer l
             for (int l = L - 1; l >= 0; --l) {
@@ -710,12 +711,176 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_force_kernel(const AtomArgs<T
             }
             for (int s = 0; s < n_sf; ++s) {
                 const T ws_ = gc[s * kMlpThreads] * (T)tab.slope[s];
+                if (a.wbuf) a.wbuf[(size_t)w * a.n_sf_max + s] = ws_;
                 fx -= ws_ * g[4 * s + 1]; fy -= ws_ * g[4 * s + 2]; fz -= ws_ * g[4 * s + 3];
             }
         }
     }
     if (a.e_atom) a.e_atom[out_row] = energy;
     if (a.forces) { a.forces[3 * out_row] = fx; a.forces[3 * out_row + 1] = fy; a.forces[3 * out_row + 2] = fz; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4. full-force mode (PANTEA_FORCE_FULL; SURVEY.md 8(f)-4, not a reference mode): F = -dE/dr of the total energy.
+//    With w_s = dE_i/dG_is from the network kernel, every centre i contributes g_in = sum_s w_s dG_is/d(d_in),
+//    d_in = r_i - r_n, to itself (F_i -= g_in) and to its neighbour n (F_n += g_in).  Unlike the central-role
+//    derivative (acsf.py:215-228) the r_jk leg of G3 does not cancel:
+//      dT/dd_ij = T_c (u_k - c u_j)/r_j + T_j u_j + T_jk u_jk,   dT/dd_ik = T_c (u_j - c u_k)/r_k + T_k u_k - T_jk u_jk
+//    (SURVEY.md Appendix A).  One warp per centre walks the radial functions and the same pre-filtered pair lists
+//    as the evaluation, accumulates g_in per neighbour in shared memory (shared atomics) and issues one global
+//    atomic per neighbour and component.  Generic over kinds / cutoffs / zeta (runtime, warp-uniform branches).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFullWarps = 4;
+
+template <typename T>
+__host__ __device__ inline size_t full_smem_bytes(int cap, int n_cls, int n_sf) {
+    const size_t t_elems = (size_t)(5 + 2 * n_cls) * cap + (size_t)3 * cap + (size_t)n_sf;
+    return ((t_elems * sizeof(T) + (size_t)cap * sizeof(int)) + 15) & ~size_t(15);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFullWarps * 32) full_force_kernel(const AtomArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * kFullWarps + wib;
+    if (w >= a.n_work) return;
+    int slot, out_row, etype;
+    if (!resolve_item(a, w, slot, out_row, etype)) return;
+    if (etype >= a.n_types || a.tables[etype].n_layers == 0) return;
+    const ElementTable& tab = a.tables[etype];
+    const Rec<T> ri = a.rec[slot];
+
+    T lx, ly, lz;
+    bool pbc;
+    item_box(a, slot, lx, ly, lz, pbc);
+    const bool wrap_jk = pbc && a.wrap_jk;
+
+    const int cap = a.scap;
+    const int stride = 5 + 2 * a.n_cls_max;
+    unsigned char* base = smem_raw + (size_t)wib * full_smem_bytes<T>(cap, a.n_cls_max, a.n_sf_max);
+    T* snb = (T*)base;                          // [cap][stride]: u_x, u_y, u_z, r, 1/r, (fc, fc') per cutoff class
+    T* sacc = snb + (size_t)stride * cap;       // [cap][3] force on each neighbour from this centre
+    T* sw = sacc + (size_t)3 * cap;             // [n_sf_max] dE_i/dG_is
+    int* sidx = (int*)(sw + a.n_sf_max);        // [cap] original atom index of each neighbour
+
+    Segments sg;
+    sg.load(a.tcount + (size_t)slot * kBuckets, cap);
+    const int total = sg.total;
+    {
+        const int32_t* row = a.nbr + (size_t)slot * a.cap;
+        const int n_cls = tab.n_cls;
+        for (int n = lane; n < total; n += 32) {
+            const Rec<T> rj = a.rec[row[n]];
+            T dx = sub_rn(ri.x, rj.x), dy = sub_rn(ri.y, rj.y), dz = sub_rn(ri.z, rj.z);
+            if (pbc) { dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz); }
+            const T r = t_sqrt<T>(dx * dx + dy * dy + dz * dz), iv = (T)1 / r;
+            T* p = snb + (size_t)n * stride;
+            p[0] = dx * iv; p[1] = dy * iv; p[2] = dz * iv; p[3] = r; p[4] = iv;
+            for (int c = 0; c < n_cls; ++c) {
+                T fc, dfc;
+                cutoff_eval_ool<T>(tab.cls[c].type, r, (T)tab.cls[c].rc, &fc, &dfc);
+                p[5 + 2 * c] = fc; p[6 + 2 * c] = dfc;
+            }
+            sacc[3 * n] = (T)0; sacc[3 * n + 1] = (T)0; sacc[3 * n + 2] = (T)0;
+            sidx[n] = rec_idx(rj);
+        }
+        for (int s = lane; s < tab.n_sf; s += 32) sw[s] = a.wbuf[(size_t)w * a.n_sf_max + s];
+    }
+    __syncwarp();
+
+    // ---- radial: g_in = sum_s w_s g_s'(r_in) u_in ; every lane owns its neighbours, no atomics ------------
+    for (int s = 0; s < tab.n_radial; ++s) {
+        const RadialSF sf = tab.radial[s];
+        const int lo = sg.lo(sf.type_j), hi = sg.hi(sf.type_j);
+        const T eta = (T)sf.eta, rs = (T)sf.r_shift, ws_ = sw[sf.out];
+        const int fco = 5 + 2 * sf.cls;
+        for (int n = lo + lane; n < hi; n += 32) {
+            const T* p = snb + (size_t)n * stride;
+            const T r = p[3], fc = p[fco], dfc = p[fco + 1];
+            T dval;
+            if (sf.kind == PANTEA_G1) dval = dfc;
+            else {
+                const T dr = r - rs, ex = t_exp<T>(-eta * dr * dr);
+                dval = ex * (dfc - (T)2 * eta * dr * fc);
+            }
+            const T c = ws_ * dval;
+            sacc[3 * n] += c * p[0]; sacc[3 * n + 1] += c * p[1]; sacc[3 * n + 2] += c * p[2];
+        }
+        __syncwarp();
+    }
+
+    // ---- angular: walk the pair lists, one triplet per lane and iteration ---------------------------------
+    {
+        const int32_t* offs = a.pair_off + (size_t)w * (a.max_groups + 1);
+        const int32_t* lists = a.pairs + (size_t)w * a.pair_cap;
+        for (int gi = 0; gi < tab.n_groups; ++gi) {
+            const AngularGroup grp = tab.groups[gi];
+            const int lo = offs[gi], count = offs[gi + 1] - lo;
+            const int fco = 5 + 2 * grp.cls;
+            const int ctype = tab.cls[grp.cls].type;
+            const T rc = (T)tab.cls[grp.cls].rc;
+            const bool is_g3 = grp.kind == PANTEA_G3;
+            for (int e = lane; e < count; e += 32) {
+                const int jk = lists[lo + e];
+                const int nj = jk & 0xffff, nk = jk >> 16;
+                const T* pj = snb + (size_t)nj * stride;
+                const T* pk = snb + (size_t)nk * stride;
+                const T uxj = pj[0], uyj = pj[1], uzj = pj[2], rj = pj[3], ivj = pj[4], fcj = pj[fco], dfj = pj[fco + 1];
+                const T uxk = pk[0], uyk = pk[1], uzk = pk[2], rk = pk[3], ivk = pk[4], fck = pk[fco], dfk = pk[fco + 1];
+                T ex = uxj * rj - uxk * rk, ey = uyj * rj - uyk * rk, ez = uzj * rj - uzk * rk;  // d_jk = d_ij - d_ik
+                if (wrap_jk) { ex = min_image(ex, lx); ey = min_image(ey, ly); ez = min_image(ez, lz); }
+                const T rjk2 = ex * ex + ey * ey + ez * ez;
+                if (!(rjk2 > (T)0)) continue;  // k == j / coincident neighbours excluded (acsf.py:325)
+                T fcjk = (T)1, dfjk = (T)0, rjk = (T)0, ivjk = (T)0, r2 = rj * rj + rk * rk;
+                if (is_g3) {
+                    rjk = t_sqrt<T>(rjk2); ivjk = (T)1 / rjk;
+                    cutoff_eval_ool<T>(ctype, rjk, rc, &fcjk, &dfjk);
+                    r2 += rjk2;
+                    if (fcjk == (T)0 && dfjk == (T)0) continue;
+                }
+                const T cost = uxj * uxk + uyj * uyk + uzj * uzk;
+                T a1 = 0, a2 = 0, a3 = 0, b1 = 0, b2 = 0;  // g_j = a1 u_j + a2 u_k + a3 u_jk ; g_k = b1 u_k + b2 u_j - a3 u_jk
+                for (int m = 0; m < grp.count; ++m) {
+                    const AngularMember mem = tab.members[grp.first + m];
+                    const T wm = sw[mem.out];
+                    const T eta = (T)mem.eta, lam = (T)mem.lambda0;
+                    const T bs = (T)1 + lam * cost;
+                    T pw1 = (T)1;
+                    if (mem.izeta != 1) pw1 = mem.izeta > 1 ? powi<T>(bs, mem.izeta - 1) : pow_general<T>(bs, (T)(mem.zeta - 1.0));
+                    const T ee = t_exp<T>(-eta * r2) * pw1 * (T)mem.pref;   // pref (1 + lambda c)^(zeta-1) exp(-eta r2)
+                    const T A = ee * bs;                                     // pref (1 + lambda c)^zeta exp(-eta r2)
+                    const T Tc = wm * (T)(mem.zeta * mem.lambda0) * ee * (fcj * fck * fcjk);
+                    const T Tj = wm * A * fck * fcjk * (dfj - (T)2 * eta * rj * fcj);
+                    const T Tk = wm * A * fcj * fcjk * (dfk - (T)2 * eta * rk * fck);
+                    a2 += Tc * ivj; a1 += Tj - Tc * cost * ivj;
+                    b2 += Tc * ivk; b1 += Tk - Tc * cost * ivk;
+                    if (is_g3) a3 += wm * A * fcj * fck * (dfjk - (T)2 * eta * rjk * fcjk);
+                }
+                const T ujx = ex * ivjk, ujy = ey * ivjk, ujz = ez * ivjk;  // u_jk (zero for G9)
+                atomicAdd(&sacc[3 * nj], a1 * uxj + a2 * uxk + a3 * ujx);
+                atomicAdd(&sacc[3 * nj + 1], a1 * uyj + a2 * uyk + a3 * ujy);
+                atomicAdd(&sacc[3 * nj + 2], a1 * uzj + a2 * uzk + a3 * ujz);
+                atomicAdd(&sacc[3 * nk], b1 * uxk + b2 * uxj - a3 * ujx);
+                atomicAdd(&sacc[3 * nk + 1], b1 * uyk + b2 * uyj - a3 * ujy);
+                atomicAdd(&sacc[3 * nk + 2], b1 * uzk + b2 * uzj - a3 * ujz);
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- scatter: F_n += g_in, F_i -= sum_n g_in --------------------------------------------------------
+    T cx = 0, cy = 0, cz = 0;
+    for (int n = lane; n < total; n += 32) {
+        const T gx = sacc[3 * n], gy = sacc[3 * n + 1], gz = sacc[3 * n + 2];
+        T* f = a.forces + (size_t)3 * sidx[n];
+        atomicAdd(f, gx); atomicAdd(f + 1, gy); atomicAdd(f + 2, gz);
+        cx += gx; cy += gy; cz += gz;
+    }
+    cx = warp_sum(cx); cy = warp_sum(cy); cz = warp_sum(cz);
+    if (lane == 0) {
+        T* f = a.forces + (size_t)3 * out_row;
+        atomicAdd(f, -cx); atomicAdd(f + 1, -cy); atomicAdd(f + 2, -cz);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -840,7 +1005,10 @@ static int ensure_pair_storage(pantea_workspace* ws) {
 
 template <typename T>
 static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32_t* centres, int64_t n_centres, void* G,
-                             void* dG, void* e_atom, void* forces, cudaStream_t st) {
+                             void* dG, void* e_atom, void* forces_out, int force_mode, cudaStream_t st) {
+    // full-force mode: the evaluation only needs values, the network kernel hands out dE_i/dG_is, a scatter pass follows
+    const bool full = forces_out != nullptr && force_mode == PANTEA_FORCE_FULL;
+    void* forces = full ? nullptr : forces_out;
     const pantea_potential* pot = ws->pot;
     int rc = ensure_pair_storage(ws);
     if (rc != PANTEA_OK) return rc;
@@ -857,7 +1025,7 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
     a.filter_guard = nullptr;
     a.tables = pot->dev; a.n_types = pot->n_elements; a.element_slot = element_slot;
     a.centres = centres;
-    const bool energy_pass = (e_atom || forces) && !G && !dG;
+    const bool energy_pass = (e_atom || forces_out) && !G && !dG;
     a.by_slot = energy_pass ? 1 : 0;
     a.own_begin = (int)ws->own_begin; a.own_end = ws->own_end < 0 ? (int)ws->n : (int)ws->own_end;
     a.owned_slots = energy_pass && ws->owned_active ? ws->owned_slots : nullptr;
@@ -865,7 +1033,17 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
     a.pairs = ws->pairs; a.pair_off = ws->pair_off; a.pair_cap = ws->pair_cap; a.max_groups = pot->max_groups;
     a.G = (T*)G; a.dG = (T*)dG; a.e_atom = (T*)e_atom; a.forces = (T*)forces;
     a.gbuf = nullptr;
-    if (e_atom || forces) {
+    a.wbuf = nullptr;
+    if (full) {
+        if (!ws->wbuf) {
+            const size_t bytes = sizeof(T) * (size_t)ws->max_atoms * (pot->max_sf > 0 ? pot->max_sf : 1);
+            cudaError_t err = cudaMalloc(&ws->wbuf, bytes);
+            ++ws->arg_epoch;
+            if (err != cudaSuccess) return fail(PANTEA_ENOMEM, std::string("network-gradient buffer: ") + cudaGetErrorString(err));
+        }
+        a.wbuf = (T*)ws->wbuf;
+    }
+    if (e_atom || forces_out) {
         if (!ws->gbuf) {
             const size_t bytes = sizeof(T) * (size_t)ws->max_atoms * (pot->max_sf > 0 ? pot->max_sf : 1) * 4;
             cudaError_t err = cudaMalloc(&ws->gbuf, bytes);
@@ -922,14 +1100,28 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
         kern<<<(a.n_work + kMlpThreads - 1) / kMlpThreads, kMlpThreads, smem, st>>>(a);
         PANTEA_LAUNCH_CHECK();
     }
+    if (full) {
+        PANTEA_CUDA_TRY(cudaMemsetAsync(forces_out, 0, sizeof(T) * 3 * (size_t)ws->n, st));
+        a.forces = (T*)forces_out;
+        const size_t smem = (size_t)kFullWarps * full_smem_bytes<T>(a.scap, a.n_cls_max, a.n_sf_max);
+        auto kern = full_force_kernel<T>;
+        static size_t configured = 0;
+        if (smem > configured) {
+            if (smem > 227 * 1024) return fail(PANTEA_EINVAL, "neighbour capacity too large for the full-force pass");
+            PANTEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        kern<<<(a.n_work + kFullWarps - 1) / kFullWarps, kFullWarps * 32, smem, st>>>(a);
+        PANTEA_LAUNCH_CHECK();
+    }
     return PANTEA_OK;
 }
 
 int atom_kernel_launch(pantea_workspace* ws, int element_slot, const int32_t* centres, int64_t n_centres, void* G,
-                       void* dG, void* e_atom, void* forces, cudaStream_t st) {
+                       void* dG, void* e_atom, void* forces, cudaStream_t st, int force_mode) {
     if (ws->cap > 0xffff) return fail(PANTEA_EINVAL, "max_neighbors must be < 65536");
-    if (ws->dtype == PANTEA_F64) return atom_kernel_typed<double>(ws, element_slot, centres, n_centres, G, dG, e_atom, forces, st);
-    return atom_kernel_typed<float>(ws, element_slot, centres, n_centres, G, dG, e_atom, forces, st);
+    if (ws->dtype == PANTEA_F64) return atom_kernel_typed<double>(ws, element_slot, centres, n_centres, G, dG, e_atom, forces, force_mode, st);
+    return atom_kernel_typed<float>(ws, element_slot, centres, n_centres, G, dG, e_atom, forces, force_mode, st);
 }
 
 }  // namespace pantea
@@ -951,11 +1143,12 @@ int pantea_acsf_compute(pantea_workspace* ws, int32_t element, const int32_t* ce
 int pantea_energy_forces(pantea_workspace* ws, void* e_atom, void* forces, void* e_total, int32_t force_mode, void* stream) {
     if (!ws || !ws->pot) return fail(PANTEA_EINVAL, "pantea_energy_forces: workspace has no potential");
     if (ws->mode == kModeNone) return fail(PANTEA_EINVAL, "pantea_energy_forces: call pantea_neighbor_build first");
-    if (force_mode != PANTEA_FORCE_REFERENCE) return fail(PANTEA_EINVAL, "pantea_energy_forces: unknown force_mode");
+    if (force_mode != PANTEA_FORCE_REFERENCE && force_mode != PANTEA_FORCE_FULL)
+        return fail(PANTEA_EINVAL, "pantea_energy_forces: unknown force_mode");
     if (!e_atom && !forces && !e_total) return fail(PANTEA_EINVAL, "pantea_energy_forces: all outputs are NULL");
     if (ws->n == 0) return PANTEA_OK;
     void* ea = e_atom ? e_atom : (e_total ? ws->md_eatom : nullptr);
-    int rc = atom_kernel_launch(ws, -1, nullptr, 0, nullptr, nullptr, ea, forces, (cudaStream_t)stream);
+    int rc = atom_kernel_launch(ws, -1, nullptr, 0, nullptr, nullptr, ea, forces, (cudaStream_t)stream, force_mode);
     if (rc != PANTEA_OK) return rc;
     if (e_total) return reduce_energy(ws, ea, e_total, (cudaStream_t)stream);
     return PANTEA_OK;

@@ -138,6 +138,7 @@ struct pantea_workspace {
     int64_t max_atoms = 0;
     int cap = 0;    // neighbours per row
     void* gbuf = nullptr;          // [max_atoms][max_sf][4] summed descriptors (evaluation -> network kernel)
+    void* wbuf = nullptr;          // [max_atoms][max_sf] dE_i/dG_is (network kernel -> full-force scatter pass)
     int32_t* pairs = nullptr;      // [max_atoms][pair_cap] pre-filtered (j,k) pair lists
     int32_t* pair_off = nullptr;   // [max_atoms][pair_groups + 1]
     int pair_cap = 0, pair_groups = 0, pair_cap_request = 0;
@@ -220,7 +221,7 @@ int neighbor_build_impl(pantea_workspace* ws, const void* pos, const int32_t* ty
                         const int32_t* struct_ptr, const double* boxes, int64_t n_structs, double rc, cudaStream_t st);
 // implemented in acsf.cu
 int atom_kernel_launch(pantea_workspace* ws, int element_slot, const int32_t* centres, int64_t n_centres, void* G,
-                       void* dG, void* e_atom, void* forces, cudaStream_t st);
+                       void* dG, void* e_atom, void* forces, cudaStream_t st, int force_mode = PANTEA_FORCE_REFERENCE);
 int reduce_energy(pantea_workspace* ws, const void* e_atom, void* e_total, cudaStream_t st);
 int ensure_cell_capacity(pantea_workspace* ws, int64_t ncells);
 }  // namespace pantea

@@ -248,7 +248,7 @@ int pantea_workspace_destroy(pantea_workspace* ws) {
     if (ws->capture_stream) cudaStreamDestroy(ws->capture_stream);
     void* ptrs[] = {ws->rec, ws->slot_of, ws->struct_of, ws->nbr, ws->nbr_tcount, ws->cell_of, ws->tmp_order,
                     ws->cell_start, ws->cell_fill, ws->flags, ws->e_partial, ws->md_forces, ws->md_eatom, ws->md_ke,
-                    ws->pairs, ws->pair_off, ws->gbuf, ws->rec_screen, ws->wide_flag, ws->pos_ref, ws->skin_flags, ws->owned_slots, ws->cell_own};
+                    ws->pairs, ws->pair_off, ws->gbuf, ws->wbuf, ws->rec_screen, ws->wide_flag, ws->pos_ref, ws->skin_flags, ws->owned_slots, ws->cell_own};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete ws;

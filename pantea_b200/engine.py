@@ -297,7 +297,7 @@ class Workspace:
         return G, dG
 
     def energy_forces(self, want_energy: bool = True, want_forces: bool = True, want_atomic: bool = False,
-                      out_forces: Optional[torch.Tensor] = None):
+                      out_forces: Optional[torch.Tensor] = None, force_mode: int = 0):
         lib = _lib.load()
         dev = self._keep[0].device
         n = self.n_atoms
@@ -307,7 +307,7 @@ class Workspace:
         if want_forces:
             forces = out_forces if out_forces is not None else torch.zeros((n, 3), dtype=self.dtype, device=dev)
         self._checked(lambda: _lib.check(lib.pantea_energy_forces(
-            self.handle, _lib.ptr(e_atom), _lib.ptr(forces), _lib.ptr(e_total), 0, _lib.stream_ptr())))
+            self.handle, _lib.ptr(e_atom), _lib.ptr(forces), _lib.ptr(e_total), int(force_mode), _lib.stream_ptr())))
         return e_total, e_atom, forces
 
 

@@ -175,12 +175,16 @@ class NeuralNetworkPotential:
         energy, _, _ = ws.energy_forces(want_energy=True, want_forces=False)
         return energy
 
-    def compute_forces(self, structure: Structure) -> Array:
-        """Force components [N, 3] (reference semantics, central-role gradient)."""
+    def compute_forces(self, structure: Structure, forces: str = "reference") -> Array:
+        """Force components [N, 3].  `forces="reference"` (default): the reference's central-role gradient
+        (`force.py:16-43`, does not sum to zero).  `forces="full"` (extension): -dE/dr of the total
+        energy including every atom's neighbour role (Newton's third law holds)."""
+        if forces not in ("reference", "full"):
+            logger.error(f"Unknown force definition '{forces}'", exception=ValueError)
         self._check_scaler_params_exist()
         ws = self._bind(structure)
-        _, _, forces = ws.energy_forces(want_energy=False, want_forces=True)
-        return forces
+        _, _, out = ws.energy_forces(want_energy=False, want_forces=True, force_mode=1 if forces == "full" else 0)
+        return out
 
     def compute_energy_and_forces(self, structure: Structure) -> Tuple[Array, Array]:
         """Extension: both results from the same fused launch."""

@@ -96,3 +96,109 @@ def test_scaler_statistics_merge_across_ranks_world2():
         np.testing.assert_allclose(mean_e, data[0::2].mean(0), rtol=1e-13)
     for k in range(1, 5):
         np.testing.assert_array_equal(res[0][k], res[1][k])        # every rank holds bitwise the same statistics
+
+
+# ---------------------------------------------------------------------------------------------- halo exchange
+def _halo_worker(rank, world, port, dims, out):
+    from pantea_b200.halo import HaloDomain
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        box, rc, n = [30.0, 24.0, 27.0], 6.0, 900
+        pos = torch.from_numpy(rng.uniform(0.0, 1.0, (n, 3)) * np.asarray(box))
+        vel = torch.from_numpy(rng.normal(size=(n, 3)))
+        types = torch.from_numpy(rng.integers(1, 3, n).astype(np.int32))
+        dom = HaloDomain(box, rc, rank, world, dims)
+        gid = torch.nonzero(dom.grid.owner(pos) == rank, as_tuple=True)[0]
+        own_pos, own_vel, own_types = pos[gid].clone(), vel[gid].clone(), types[gid].clone()
+        res = {}
+        for phase in range(2):
+            n_ghost = dom.build_lists(own_pos)
+            ghost_pos, ghost_gid = dom.forward(own_pos), dom.forward(gid)
+            assert ghost_pos.shape[0] == n_ghost == dom.n_ghost
+            # reverse halo: every ghost row returns 1 -> an owned atom collects its number of ghost copies
+            back = dom.reverse(torch.ones((n_ghost, 1), dtype=torch.float64))
+            copies = torch.zeros(len(gid), dtype=torch.float64).index_add_(0, dom.send_idx, back[:, 0])
+            occ = (dom.rev_first[1:] - dom.rev_first[:-1]).double()
+            res[phase] = (gid.numpy().copy(), own_pos.numpy().copy(), own_vel.numpy().copy(), own_types.numpy().copy(),
+                          ghost_gid.numpy().copy(), ghost_pos.numpy().copy(), copies.numpy().copy(),
+                          bool(torch.equal(copies, occ)),
+                          dom.gather_global(own_vel, gid, n).numpy().copy(), pos.numpy().copy())
+            # every atom moves (same draw on every rank), is wrapped, and migrates to its new brick
+            step = torch.from_numpy(np.random.default_rng(77).normal(scale=2.0, size=(n, 3)))
+            pos = torch.remainder(pos + step, torch.tensor(box, dtype=torch.float64))
+            own_pos = pos[gid].clone()
+            (own_pos, own_vel, own_types), gid = dom.migrate(own_pos, [own_pos, own_vel, own_types], gid)
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dims", [(2, 1, 1), (1, 1, 2)])
+def test_halo_domain_migration_and_ghosts_world2(dims):
+    """brick ownership, ghost selection, forward / reverse halo and migration on 2 ranks (gloo, CPU)."""
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_halo_worker, args=(world, _free_port(), dims, out), nprocs=world, join=True)
+        res = dict(out)
+    rng = np.random.default_rng(5)
+    box, rc, n = np.asarray([30.0, 24.0, 27.0]), 6.0, 900
+    pos = rng.uniform(0.0, 1.0, (n, 3)) * box
+    vel = rng.normal(size=(n, 3))
+    types = rng.integers(1, 3, n).astype(np.int32)
+    for phase in range(2):
+        if phase == 1:
+            pos = res[0][phase][9]
+            assert not np.array_equal(res[0][0][0], res[0][1][0])                 # atoms did change owner
+        gids = [res[r][phase][0] for r in range(world)]
+        assert sorted(np.concatenate(gids).tolist()) == list(range(n))          # every atom has exactly one owner
+        d = pos[:, None, :] - pos[None, :, :]
+        d -= box * np.rint(d / box)
+        within = (d ** 2).sum(-1) <= rc * rc
+        for r in range(world):
+            gid, own_pos, own_vel, own_types, ghost_gid, ghost_pos, copies, rev_ok, vel_all, _ = res[r][phase]
+            np.testing.assert_array_equal(own_pos, pos[gid])                      # payloads follow their atoms
+            np.testing.assert_array_equal(own_vel, vel[gid])
+            np.testing.assert_array_equal(own_types, types[gid])
+            np.testing.assert_array_equal(ghost_pos, pos[ghost_gid])
+            np.testing.assert_array_equal(vel_all, vel)
+            assert rev_ok and len(set(ghost_gid.tolist())) == len(ghost_gid) and not set(ghost_gid) & set(gid)
+            local = set(gid.tolist()) | set(ghost_gid.tolist())
+            needed = set(np.nonzero(within[gid].any(0))[0].tolist())             # anything within rc of an owned atom
+            assert needed <= local
+            other = 1 - r
+            np.testing.assert_array_equal(copies, np.isin(gid, res[other][phase][4]).astype(float))
+
+
+@pytest.mark.parametrize("world,expect", [(8, (2, 2, 2)), (4, (2, 2, 1)), (2, (2, 1, 1)), (6, (3, 2, 1)), (1, (1, 1, 1))])
+def test_brick_grid_covers_every_neighbour(world, expect):
+    """Ghost criterion of the brick decomposition: owned + ghost atoms of a brick contain every atom within rc (minimum
+    image) of an owned atom; ownership is a partition.  Pure host logic, no collective."""
+    from pantea_b200.halo import BrickGrid
+    rng = np.random.default_rng(11)
+    box, rc, n = np.asarray([26.0, 26.0, 26.0]), 6.0, 1500
+    grid = BrickGrid(box.tolist(), world)
+    assert grid.dims == expect
+    pos = torch.from_numpy(rng.uniform(0.0, 1.0, (n, 3)) * box)
+    pos[:8] = torch.tensor([[0.0, 0.0, 0.0], [13.0, 13.0, 13.0], [25.999999999, 0.0, 13.0], [12.999999999, 13.0, 0.0],
+                            [13.0, 0.0, 25.999999999], [6.0, 19.0, 13.0], [19.0, 6.0, 7.0], [7.0, 6.0, 19.0]])
+    owner = grid.owner(pos)
+    assert owner.min() >= 0 and owner.max() < world
+    d = pos[:, None, :] - pos[None, :, :]
+    d -= torch.from_numpy(box) * torch.round(d / torch.from_numpy(box))
+    within = (d ** 2).sum(-1) <= rc * rc
+    n_ghost = 0
+    for r in range(world):
+        own = owner == r
+        lo, hi = grid.bounds(r)
+        for k in range(3):
+            assert (pos[own, k] >= lo[k] - 1e-9).all() and (pos[own, k] <= hi[k] + 1e-9).all()
+        ghost = grid.ghost_mask(pos, owner, r, rc)
+        assert not (ghost & own).any()
+        needed = within[own].any(0)
+        assert not (needed & ~(own | ghost)).any()
+        n_ghost += int(ghost.sum())
+    if world == 1:
+        assert n_ghost == 0
