@@ -54,6 +54,11 @@ def parse_args():
     ap.add_argument("--kernel-times", action="store_true",
                     help="after the timed region, print a per-kernel breakdown (CUPTI, diagnostic only) to stderr")
     ap.add_argument("--no-flush", action="store_true", help="diagnostics only: skip the L2 flush between steps")
+    ap.add_argument("--halo", default="auto", choices=["auto", "on", "off"],
+                    help="secondary measurement `halo_exchange`: the same K steps with the brick-decomposed HaloMD "
+                         "(ghost-atom exchange); auto = when N > 1")
+    ap.add_argument("--halo-skin", type=float, default=1.0, help="ghost-shell skin (Bohr) of the halo measurement")
+    ap.add_argument("--halo-every", type=int, default=2, help="ghost lists rebuilt every this many steps")
     args = ap.parse_args()
     args.atoms = 3 * (args.atoms // 3)  # whole water molecules: "100 000 atoms" = 33 333 molecules = 99 999 atoms
     return args
@@ -208,11 +213,11 @@ def run_b200(args) -> None:
     pos0, vel0 = md.pos.clone(), md.vel.clone()
     max_seen = 0
 
-    def capacity_ok() -> bool:
+    def capacity_ok(m=None) -> bool:
         nonlocal max_seen
         bad = 0.0
         try:
-            max_seen = max(max_seen, md.check_capacity())
+            max_seen = max(max_seen, (m or md).check_capacity())
         except _lib.CapacityError:
             bad = 1.0
         flag = torch.tensor([bad], dtype=torch.float64, device=dev)
@@ -223,23 +228,25 @@ def run_b200(args) -> None:
     warmup = max(warmup, SEGMENT)
     launches_per_reset = 0
 
-    def settle_capacities() -> None:
+    def settle_capacities(m=None) -> None:
         """Untimed: run one full segment until no capacity flag is raised (the library grows its buffers), then reset."""
         nonlocal launches_per_reset
+        m = m or md
         for attempt in range(6):
             for _ in range(warmup):
-                md.step()
-            ok = capacity_ok()  # on overflow the library has raised the capacity: run the segment again
+                m.step()
+            ok = capacity_ok(m)  # on overflow the library has raised the capacity: run the segment again
             l0 = lib.pantea_launch_count()
-            md.reset(pos0, vel0)
+            m.reset(pos0, vel0)
             launches_per_reset = lib.pantea_launch_count() - l0
             if ok:
                 return
         raise SystemExit("bench.py: capacities did not settle")
 
-    def timed_steps(k_steps: int):
+    def timed_steps(k_steps: int, m=None):
         """K steps, each bracketed by CUDA events on the launching stream (L2 flushed before each); returns the summed
         step time (ms, max over ranks), the wall time and the kernels launched by the steps themselves."""
+        m = m or md
         barrier()
         launches0 = lib.pantea_launch_count()
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(k_steps)]
@@ -248,12 +255,12 @@ def run_b200(args) -> None:
         wall0 = time.perf_counter()
         for k in range(k_steps):
             if k > 0 and k % SEGMENT == 0:
-                md.reset(pos0, vel0)
+                m.reset(pos0, vel0)
                 extra_launches += launches_per_reset
             flush()
             extra_launches += 0 if args.no_flush else 1
             starts[k].record()
-            md.step()
+            m.step()
             stops[k].record()
         barrier()
         wall_s = time.perf_counter() - wall0
@@ -292,6 +299,33 @@ def run_b200(args) -> None:
         md.ws.set_skin(0.0)
         md.reset(pos0, vel0)
         settle_capacities()
+
+    # ---- secondary measurement: brick decomposition with ghost-atom halo exchange -----------------
+    # same K steps, same segments; the headline stays the replicated-coordinates scheme until the halo path wins
+    halo_info = None
+    if args.halo == "on" or (args.halo == "auto" and world > 1):
+        from pantea_b200.halo import HaloMD
+        pos_full = t(pos_h)  # HaloMD takes the full initial arrays on every rank and keeps its brick
+        vel_full = t(vel_h)
+        hmd = HaloMD(pot, pos_full, vel_full, t(mass_h), t(types_h, torch.int32), box, DT, rank, world,
+                     skin=args.halo_skin if args.halo_every > 1 else 0.0, rebuild_every=args.halo_every)
+        pos0_keep, vel0_keep = pos0, vel0
+        pos0, vel0 = pos_full, vel_full
+        settle_capacities(hmd)
+        ms_halo, _, halo_launches = timed_steps(args.steps, hmd)
+        hmd.validate()
+        if not capacity_ok(hmd):
+            raise SystemExit("bench.py: a capacity flag was raised inside the halo-exchange timed region")
+        shares = torch.tensor([float(hmd.n_own), float(hmd.n_ghost)], dtype=torch.float64, device=dev)
+        all_reduce_max(shares)
+        halo_info = {"value": n * args.steps / (ms_halo * 1e-3), "unit": UNIT, "ms_per_step": ms_halo / args.steps,
+                     "bricks": list(hmd.domain.grid.dims), "skin_bohr": hmd.skin, "rebuild_every": hmd.rebuild_every,
+                     "rebuilds": hmd.rebuilds, "rollbacks": hmd.rollbacks, "max_owned_per_rank": int(shares[0].item()),
+                     "max_ghosts_per_rank": int(shares[1].item()), "gpu_launches": int(halo_launches),
+                     "what": "same K steps with brick decomposition: ghost positions by one all_to_all_single per step "
+                             "(fixed lists between rebuilds), migration + list rebuild every `rebuild_every` steps"}
+        pos0, vel0 = pos0_keep, vel0_keep
+        del hmd
 
     if args.kernel_times and rank == 0:  # diagnostic: never feeds a reported number
         from torch.profiler import ProfilerActivity, profile
@@ -423,7 +457,7 @@ def run_b200(args) -> None:
                        "max_neighbors_seen": int(mx.value), "force_mode": "reference (central-role gradient)",
                        "trajectory": f"timed steps replay {SEGMENT}-step segments from the initial state (untimed reset)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "verlet_skin": skin_info,
+            "verlet_skin": skin_info, "halo_exchange": halo_info,
             "wall_s_timed_region": wall,
         }
         line.update(extra)

@@ -1,10 +1,14 @@
 """Multi-GPU invariance check (run under torchrun on N GPUs; not collected by pytest):
 
     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/mgpu_check.py [atoms] [steps]
+    torchrun ... tests/mgpu_check.py [atoms] [steps] halo [skin] [rebuild_every] [full]
 
 Runs the same water box with ReplicatedMD on N ranks and, on rank 0, on a single rank; requires identical
 neighbour sets implicitly through bitwise identical positions / velocities / forces after `steps` MD steps
 (per-atom results do not depend on the ownership split: same kernels, same per-atom arithmetic and order).
+With `halo` the N-rank run is the brick-decomposed HaloMD (ghost-atom exchange over NCCL, migration); the neighbour
+order inside a row then differs from the single-GPU one, so agreement is required to 1e-10 relative,
+not bitwise.  `full` selects PANTEA_FORCE_FULL (reverse halo).
 """
 import sys
 from pathlib import Path
@@ -21,9 +25,59 @@ from pantea_b200.potentials import NeuralNetworkPotential  # noqa: E402
 from pantea_b200.utils.synthetic import md_velocities, water_box, water_masses  # noqa: E402
 
 
+def main_halo(n_atoms, steps, skin, every, full):
+    from pantea_b200.halo import HaloMD
+    rank, world, local = init_distributed()
+    dev = torch.device("cuda", local)
+    nnp = NeuralNetworkPotential.from_runner(ROOT / "tests" / "golden" / "h2o.json")
+    nnp.load()
+    pot = nnp.device_potential()
+    pos, types, box = water_box(n_atoms)
+    vel, mass = md_velocities(types), water_masses(types)
+    t = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)  # noqa: E731
+    args = (pot, t(pos), t(vel), t(mass), t(types, torch.int32), list(box), 0.25)
+    md = HaloMD(*args, rank, world, skin=skin, rebuild_every=every, force_mode=1 if full else 0)
+    for _ in range(steps):
+        md.step()
+    md.validate()
+    md.check_capacity()
+    e_pot, e_kin = float(md.potential_energy()), float(md.kinetic_energy())
+    pos_all, vel_all, frc_all = md.gather_owned(md.pos), md.gather_owned(md.vel), md.gather_owned(md.frc)
+    counts = torch.tensor([md.n_own, md.n_ghost], dtype=torch.float64, device=dev)
+    gathered = [torch.zeros_like(counts) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(gathered, counts)
+    torch.cuda.synchronize()
+    if rank == 0:
+        ref = HaloMD(*args, 0, 1, force_mode=1 if full else 0)   # one brick, no ghosts: the single-GPU path
+        for _ in range(steps):
+            ref.step()
+        ref.check_capacity()
+        rp, rv, rf = ref.gather_owned(ref.pos), ref.gather_owned(ref.vel), ref.gather_owned(ref.frc)
+        d = pos_all - rp
+        bx = torch.tensor(list(box), dtype=torch.float64, device=dev)
+        d -= bx * torch.round(d / bx)
+        e_ref, k_ref = float(ref.potential_energy()), float(ref.kinetic_energy())
+        err = (float(d.abs().max()), float((vel_all - rv).abs().max() / rv.abs().max()),
+               float((frc_all - rf).abs().max() / rf.abs().max()))
+        print(f"halo world={world} dims={md.domain.grid.dims} atoms={n_atoms} steps={steps} skin={skin} every={every} "
+              f"full={full} owned/ghosts per rank={[tuple(int(x) for x in g.tolist()) for g in gathered]} "
+              f"rebuilds={md.rebuilds} rollbacks={md.rollbacks} max|dx|={err[0]:.3e} rel dv={err[1]:.3e} rel dF={err[2]:.3e} "
+              f"dEpot={abs(e_pot - e_ref):.3e} dEkin={abs(e_kin - k_ref):.3e}")
+        assert err[0] < 1e-9 and err[1] < 1e-9 and err[2] < 1e-8
+        assert abs(e_pot - e_ref) < 1e-9 * abs(e_ref) and abs(e_kin - k_ref) < 1e-9 * abs(k_ref)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     n_atoms = int(sys.argv[1]) if len(sys.argv) > 1 else 24000
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    if len(sys.argv) > 3 and sys.argv[3] == "halo":
+        skin = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
+        every = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+        return main_halo(n_atoms, steps, skin, every, len(sys.argv) > 6 and sys.argv[6] == "full")
     rank, world, local = init_distributed()
     dev = torch.device("cuda", local)
     nnp = NeuralNetworkPotential.from_runner(ROOT / "tests" / "golden" / "h2o.json")
