@@ -54,9 +54,9 @@ def parse_args():
     ap.add_argument("--kernel-times", action="store_true",
                     help="after the timed region, print a per-kernel breakdown (CUPTI, diagnostic only) to stderr")
     ap.add_argument("--no-flush", action="store_true", help="diagnostics only: skip the L2 flush between steps")
-    ap.add_argument("--halo", default="auto", choices=["auto", "on", "off"],
+    ap.add_argument("--halo", default="off", choices=["auto", "on", "off"],
                     help="secondary measurement `halo_exchange`: the same K steps with the brick-decomposed HaloMD "
-                         "(ghost-atom exchange); auto = when N > 1")
+                         "(ghost-atom exchange); auto = when N > 1 (default off: opt-in)")
     ap.add_argument("--halo-skin", type=float, default=1.0, help="ghost-shell skin (Bohr) of the halo measurement")
     ap.add_argument("--halo-every", type=int, default=2, help="ghost lists rebuilt every this many steps")
     args = ap.parse_args()
@@ -312,15 +312,21 @@ def run_b200(args) -> None:
         pos0_keep, vel0_keep = pos0, vel0
         pos0, vel0 = pos_full, vel_full
         settle_capacities(hmd)
+        hmd.rebuild_events = []
+        rb0, rl0 = hmd.rebuilds, hmd.rollbacks
         ms_halo, _, halo_launches = timed_steps(args.steps, hmd)
         hmd.validate()
+        torch.cuda.synchronize()
+        rebuild_ms = [a.elapsed_time(b) for a, b in hmd.rebuild_events]
         if not capacity_ok(hmd):
             raise SystemExit("bench.py: a capacity flag was raised inside the halo-exchange timed region")
         shares = torch.tensor([float(hmd.n_own), float(hmd.n_ghost)], dtype=torch.float64, device=dev)
         all_reduce_max(shares)
         halo_info = {"value": n * args.steps / (ms_halo * 1e-3), "unit": UNIT, "ms_per_step": ms_halo / args.steps,
                      "bricks": list(hmd.domain.grid.dims), "skin_bohr": hmd.skin, "rebuild_every": hmd.rebuild_every,
-                     "rebuilds": hmd.rebuilds, "rollbacks": hmd.rollbacks, "max_owned_per_rank": int(shares[0].item()),
+                     "rebuilds": hmd.rebuilds - rb0, "rollbacks": hmd.rollbacks - rl0,
+                     "rebuild_ms_mean": statistics.mean(rebuild_ms) if rebuild_ms else None,
+                     "max_owned_per_rank": int(shares[0].item()),
                      "max_ghosts_per_rank": int(shares[1].item()), "gpu_launches": int(halo_launches),
                      "what": "same K steps with brick decomposition: ghost positions by one all_to_all_single per step "
                              "(fixed lists between rebuilds), migration + list rebuild every `rebuild_every` steps"}

@@ -53,14 +53,41 @@ def brick_dims(world: int, box: Sequence[float]) -> Tuple[int, int, int]:
 
 
 class BrickGrid:
-    """`px x py x pz` bricks of a periodic orthorhombic box; rank = (ix * py + iy) * pz + iz."""
+    """`px x py x pz` bricks of a periodic orthorhombic box; rank = (ix * py + iy) * pz + iz.  `cuts[d]` are the
+    `p_d - 1` interior brick boundaries along d (ascending; default: equal widths) -- `balanced()` places them at the
+    atom-count quantiles of a configuration, which evens out the owned atoms when the density varies along an axis."""
 
-    def __init__(self, box: Sequence[float], world: int, dims: Optional[Sequence[int]] = None) -> None:
+    def __init__(self, box: Sequence[float], world: int, dims: Optional[Sequence[int]] = None,
+                 cuts: Optional[Sequence[Sequence[float]]] = None) -> None:
         self.box = [float(b) for b in box]
         self.world = int(world)
         self.dims = tuple(int(d) for d in dims) if dims is not None else brick_dims(self.world, self.box)
         if self.dims[0] * self.dims[1] * self.dims[2] != self.world:
             raise ValueError(f"brick grid {self.dims} does not match {self.world} ranks")
+        if cuts is None:
+            cuts = [[k * self.box[d] / self.dims[d] for k in range(1, self.dims[d])] for d in range(3)]
+        self.cuts = [[float(c) for c in cuts[d]] for d in range(3)]
+        for d in range(3):
+            if len(self.cuts[d]) != self.dims[d] - 1 or sorted(self.cuts[d]) != self.cuts[d]:
+                raise ValueError(f"cuts[{d}] must hold {self.dims[d] - 1} ascending boundaries")
+        self.edges = [[0.0, *self.cuts[d], self.box[d]] for d in range(3)]
+        self._cache = {}
+
+    @classmethod
+    def balanced(cls, box: Sequence[float], world: int, positions: torch.Tensor,
+                 dims: Optional[Sequence[int]] = None) -> "BrickGrid":
+        """Brick boundaries at the k / p_d quantiles of the atoms' (wrapped) coordinates along every cut axis."""
+        grid = cls(box, world, dims)
+        cuts = []
+        for d in range(3):
+            p = grid.dims[d]
+            if p == 1:
+                cuts.append([])
+                continue
+            x = torch.sort(positions[:, d].double()).values
+            n = x.numel()
+            cuts.append([float(x[min(n - 1, (k * n) // p)]) for k in range(1, p)])
+        return cls(box, world, grid.dims, cuts)
 
     def coords(self, rank: int) -> Tuple[int, int, int]:
         px, py, pz = self.dims
@@ -68,45 +95,62 @@ class BrickGrid:
 
     def bounds(self, rank: int) -> Tuple[List[float], List[float]]:
         c = self.coords(rank)
-        lo = [c[d] * self.box[d] / self.dims[d] for d in range(3)]
-        hi = [(c[d] + 1) * self.box[d] / self.dims[d] for d in range(3)]
-        return lo, hi
+        return [self.edges[d][c[d]] for d in range(3)], [self.edges[d][c[d] + 1] for d in range(3)]
+
+    def _tensors(self, device):
+        key = str(device)
+        if key not in self._cache:
+            lo = torch.tensor([self.bounds(r)[0] for r in range(self.world)], dtype=torch.float64, device=device)
+            hi = torch.tensor([self.bounds(r)[1] for r in range(self.world)], dtype=torch.float64, device=device)
+            cuts = [torch.tensor(self.cuts[d], dtype=torch.float64, device=device) for d in range(3)]
+            self._cache[key] = (lo, hi, cuts, torch.arange(self.world, device=device))
+        return self._cache[key]
 
     def owner(self, pos: torch.Tensor) -> torch.Tensor:
-        """Owning rank of every (wrapped) position: single-valued, so every atom has exactly one owner."""
+        """Owning rank of every (wrapped) position: single-valued, so every atom has exactly one owner
+        (a coordinate equal to a boundary belongs to the upper brick)."""
+        _, _, cuts, _ = self._tensors(pos.device)
         idx = []
         for d in range(3):
-            p = self.dims[d]
-            i = torch.floor(pos[:, d].double() * (p / self.box[d])).long().clamp_(0, p - 1)
-            idx.append(i)
+            if self.dims[d] == 1:
+                idx.append(torch.zeros(pos.shape[0], dtype=torch.int64, device=pos.device))
+            else:
+                idx.append(torch.bucketize(torch.remainder(pos[:, d].double(), self.box[d]).contiguous(), cuts[d], right=True))
         return (idx[0] * self.dims[1] + idx[1]) * self.dims[2] + idx[2]
 
-    def distance2(self, pos: torch.Tensor, rank: int) -> torch.Tensor:
-        """Squared periodic distance of every position to the brick of `rank` (0 inside)."""
-        lo, hi = self.bounds(rank)
-        d2 = torch.zeros(pos.shape[0], dtype=torch.float64, device=pos.device)
+    def distance2_all(self, pos: torch.Tensor) -> torch.Tensor:
+        """[world, n] squared periodic distances of every position to every brick (0 inside)."""
+        lo, hi, _, _ = self._tensors(pos.device)
+        d2 = torch.zeros((self.world, pos.shape[0]), dtype=torch.float64, device=pos.device)
         for d in range(3):
             if self.dims[d] == 1:
-                continue  # the brick spans the whole (periodic) box along d
-            x, L = pos[:, d].double(), self.box[d]
-            inside = (x >= lo[d]) & (x < hi[d])
-            gap = torch.minimum(torch.remainder(lo[d] - x, L), torch.remainder(x - hi[d], L))
-            gap = torch.where(inside, torch.zeros_like(gap), gap)
+                continue  # the bricks span the whole (periodic) box along d
+            x, L = pos[:, d].double()[None, :], self.box[d]
+            l, h = lo[:, d, None], hi[:, d, None]
+            gap = torch.minimum(torch.remainder(l - x, L), torch.remainder(x - h, L))
+            gap = torch.where((x >= l) & (x < h), torch.zeros_like(gap), gap)
             d2 += gap * gap
         return d2
 
-    def ghost_mask(self, pos: torch.Tensor, owner: torch.Tensor, rank: int, r_halo: float) -> torch.Tensor:
-        """Atoms not owned by `rank` that its brick needs as ghosts (within r_halo, slightly inclusive)."""
+    def distance2(self, pos: torch.Tensor, rank: int) -> torch.Tensor:
+        return self.distance2_all(pos)[rank]
+
+    def ghost_masks(self, pos: torch.Tensor, owner: torch.Tensor, r_halo: float) -> torch.Tensor:
+        """[world, n]: atom needed as a ghost by brick r = not owned by r and within r_halo of it (slightly inclusive)."""
         lim = r_halo * (1.0 + 1e-12) + 1e-12
-        return (owner != rank) & (self.distance2(pos, rank) <= lim * lim)
+        ranks = self._tensors(pos.device)[3]
+        return (owner[None, :] != ranks[:, None]) & (self.distance2_all(pos) <= lim * lim)
+
+    def ghost_mask(self, pos: torch.Tensor, owner: torch.Tensor, rank: int, r_halo: float) -> torch.Tensor:
+        return self.ghost_masks(pos, owner, r_halo)[rank]
 
 
 class HaloDomain:
     """Ownership, migration and ghost lists of one rank (host logic; tensors may live on any device)."""
 
     def __init__(self, box: Sequence[float], r_halo: float, rank: int, world: int,
-                 dims: Optional[Sequence[int]] = None, group=None) -> None:
-        self.grid = BrickGrid(box, world, dims)
+                 dims: Optional[Sequence[int]] = None, group=None, grid: Optional[BrickGrid] = None) -> None:
+        self.grid = grid if grid is not None else BrickGrid(box, world, dims)
         self.r_halo, self.rank, self.world, self.group = float(r_halo), int(rank), int(world), group
         self.send_idx: Optional[torch.Tensor] = None
         self.send_splits: List[int] = [0] * world
@@ -138,22 +182,39 @@ class HaloDomain:
     # ------------------------------------------------------------------------------ migration
     def migrate(self, pos_owned: torch.Tensor, arrays: Sequence[torch.Tensor], gid: torch.Tensor):
         """Send every owned atom to the rank whose brick holds its (wrapped) position.  `arrays` are per-atom arrays
-        (first axis = owned atoms); returns the new arrays and global ids, ordered by global id."""
+        (first axis = owned atoms); returns the new arrays and global ids (arrival order: by source rank, stable).
+        Two payload messages per peer: all floating-point columns in one, all integer columns (and the ids) in one."""
         if self.world == 1:
             return list(arrays), gid
+        n = int(pos_owned.shape[0])
         dest = self.grid.owner(pos_owned)
         order = torch.argsort(dest, stable=True)
         send = [int(x) for x in torch.bincount(dest, minlength=self.world).tolist()]
         recv = self.exchange_counts(send, pos_owned.device)
-        new_gid = self.all_to_all_rows(gid[order], send, recv)
-        perm = torch.argsort(new_gid)
-        out = [self.all_to_all_rows(a[order], send, recv)[perm] for a in arrays]
-        return out, new_gid[perm]
+        fl = [i for i, a in enumerate(arrays) if a.is_floating_point()]
+        it = [i for i, a in enumerate(arrays) if not a.is_floating_point()]
+        out: List[Optional[torch.Tensor]] = [None] * len(arrays)
+        if fl:
+            cols = torch.cat([arrays[i].reshape(n, -1) for i in fl], dim=1)[order]
+            got = self.all_to_all_rows(cols, send, recv)
+            c0 = 0
+            for i in fl:
+                w = arrays[i].reshape(n, -1).shape[1]
+                out[i] = got[:, c0:c0 + w].reshape(-1, *arrays[i].shape[1:]).contiguous()
+                c0 += w
+        cols = torch.cat([gid.reshape(n, 1)] + [arrays[i].reshape(n, -1).to(torch.int64) for i in it], dim=1)[order]
+        got = self.all_to_all_rows(cols, send, recv)
+        c0 = 1
+        for i in it:
+            w = arrays[i].reshape(n, -1).shape[1]
+            out[i] = got[:, c0:c0 + w].reshape(-1, *arrays[i].shape[1:]).to(arrays[i].dtype).contiguous()
+            c0 += w
+        return out, got[:, 0].contiguous()
 
     # ------------------------------------------------------------------------------ ghost lists
     def build_lists(self, pos_owned: torch.Tensor) -> int:
-        """Select, per destination rank, the owned atoms its brick needs as ghosts; exchange the counts.  Returns the
-        number of ghosts this rank receives."""
+        """Select, per destination rank, the owned atoms its brick needs as ghosts (one batched distance evaluation and
+        one compaction for all destinations); exchange the counts.  Returns the number of ghosts this rank receives."""
         n_own = int(pos_owned.shape[0])
         dev = pos_owned.device
         if self.world == 1:
@@ -161,22 +222,24 @@ class HaloDomain:
             self.send_splits, self.recv_splits = [0], [0]
         else:
             mine = torch.full((n_own,), self.rank, dtype=torch.int64, device=dev)
-            parts = []
-            for r in range(self.world):
-                if r == self.rank:
-                    parts.append(torch.zeros(0, dtype=torch.int64, device=dev))
-                else:
-                    parts.append(torch.nonzero(self.grid.ghost_mask(pos_owned, mine, r, self.r_halo), as_tuple=True)[0])
-            self.send_idx = torch.cat(parts)
-            self.send_splits = [int(p.numel()) for p in parts]
+            dst, idx = torch.nonzero(self.grid.ghost_masks(pos_owned, mine, self.r_halo), as_tuple=True)  # sorted by dst
+            self.send_idx = idx.contiguous()
+            self.send_splits = [int(x) for x in torch.bincount(dst, minlength=self.world).tolist()]
             self.recv_splits = self.exchange_counts(self.send_splits, dev)
-        # reverse halo: occurrences of every owned atom in the send list, grouped by atom
-        self.rev_order = torch.argsort(self.send_idx, stable=True)
-        first = torch.zeros(n_own + 1, dtype=torch.int64, device=dev)
-        if self.send_idx.numel():
-            first[1:] = torch.cumsum(torch.bincount(self.send_idx, minlength=n_own), 0)
-        self.rev_first = first
+        self.rev_order = self.rev_first = None
+        self._n_own = n_own
         return int(sum(self.recv_splits))
+
+    def reverse_index(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(order, first) of the reverse halo: send-list entries sorted by owned atom and each atom's range in them."""
+        if self.rev_order is None:
+            dev = self.send_idx.device
+            self.rev_order = torch.argsort(self.send_idx, stable=True)
+            first = torch.zeros(self._n_own + 1, dtype=torch.int64, device=dev)
+            if self.send_idx.numel():
+                first[1:] = torch.cumsum(torch.bincount(self.send_idx, minlength=self._n_own), 0)
+            self.rev_first = first
+        return self.rev_order, self.rev_first
 
     @property
     def n_send(self) -> int:
@@ -212,12 +275,13 @@ class HaloDomain:
 class HaloMD:
     """Velocity-Verlet MD (reference integrator, no mass: `molecular_dynamics.py:16-30`) of one periodic box on
     `world` GPUs with brick decomposition and ghost-atom halo exchange.  Same interface as `ReplicatedMD`; the full
-    initial arrays are passed to every rank, which keeps only the atoms of its brick."""
+    initial arrays are passed to every rank, which keeps only the atoms of its brick.  `balance=True` places the brick
+    boundaries at the atom-count quantiles of the initial configuration."""
 
     def __init__(self, device_potential, positions: torch.Tensor, velocities: torch.Tensor, masses: torch.Tensor,
                  types: torch.Tensor, box: Sequence[float], time_step: float, rank: int = 0, world: int = 1,
                  thermostat=None, kb: float = 3.166811563e-6, skin: float = 0.0, rebuild_every: int = 1,
-                 dims: Optional[Sequence[int]] = None, force_mode: int = 0) -> None:
+                 dims: Optional[Sequence[int]] = None, force_mode: int = 0, balance: bool = True) -> None:
         from pantea_b200 import _lib, engine
 
         self._lib, self.lib, self._engine = _lib, _lib.load(), engine
@@ -234,13 +298,17 @@ class HaloMD:
         self.dtype, self.code = positions.dtype, _lib.dtype_code(positions.dtype)
         self.dev = positions.device
         self.thermostat, self.kb = thermostat, kb
-        self.skin, self.rebuild_every, self.force_mode = float(skin), int(rebuild_every), int(force_mode)
-        self.domain = HaloDomain(self.box, device_potential.r_cutoff + self.skin, rank, world, dims)
+        self.skin, self.force_mode = float(skin), int(force_mode)
+        self.rebuild_every = self._every0 = int(rebuild_every)
+        grid = (BrickGrid.balanced(self.box, world, positions, dims) if balance and world > 1
+                else BrickGrid(self.box, world, dims))
+        self.domain = HaloDomain(self.box, device_potential.r_cutoff + self.skin, rank, world, grid=grid)
         self.ke = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.violated = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.ws = None
         self.rebuilds = 0
         self.rollbacks = 0
+        self.rebuild_events = None  # set to a list to collect (start, stop) CUDA events around every rebuild (diagnostic)
         self._global0 = (masses.reshape(-1).to(self.dtype), types.to(torch.int32))
         self.reset(positions, velocities)
 
@@ -251,37 +319,37 @@ class HaloMD:
         pos = positions.to(self.dtype)
         mine = torch.nonzero(self.domain.grid.owner(pos) == self.rank, as_tuple=True)[0]
         self.gid = mine
-        self.n_own = int(mine.numel())
-        self._own = {"pos": pos[mine].contiguous(), "vel": velocities[mine].to(self.dtype).contiguous(),
-                     "frc": torch.zeros((self.n_own, 3), dtype=self.dtype, device=self.dev),
-                     "mass": masses[mine].contiguous(), "types": types[mine].contiguous()}
+        n_own = int(mine.numel())
         self.steps = 0
         self._since = 0
-        self._install(self._own)
+        self.rebuild_every = self._every0
+        self._install(pos[mine].contiguous(), velocities[mine].to(self.dtype).contiguous(),
+                      torch.zeros((n_own, 3), dtype=self.dtype, device=self.dev), masses[mine].contiguous(),
+                      types[mine].contiguous())
         self._evaluate(first=True)
-        self.frc[: self.n_own].copy_(self.frc_new[: self.n_own])
+        self.frc[:n_own].copy_(self.frc_new[:n_own])
         self._snapshot()
 
-    def _install(self, own: dict) -> None:
-        """Build the ghost lists for the owned arrays `own` and allocate the local [owned | ghost] arrays."""
-        dom, n_own = self.domain, int(own["pos"].shape[0])
-        n_ghost = dom.build_lists(own["pos"])
+    def _install(self, pos: torch.Tensor, vel: torch.Tensor, frc: torch.Tensor, mass: torch.Tensor,
+                 types: torch.Tensor) -> None:
+        """Build the ghost lists for the given owned arrays and set up the local [owned | ghost] arrays."""
+        dom, n_own = self.domain, int(pos.shape[0])
+        n_ghost = dom.build_lists(pos)
         n_loc = n_own + n_ghost
         self.n_own, self.n_ghost, self.n_local = n_own, n_ghost, n_loc
         self.pos = torch.empty((n_loc, 3), dtype=self.dtype, device=self.dev)
-        self.pos[:n_own] = own["pos"]
+        self.pos[:n_own] = pos
         self.types = torch.empty(n_loc, dtype=torch.int32, device=self.dev)
-        self.types[:n_own] = own["types"]
-        self.vel, self.mass = own["vel"], own["mass"]
-        self.frc = torch.zeros((n_loc, 3), dtype=self.dtype, device=self.dev)
-        self.frc[:n_own] = own["frc"]
-        self.frc_new = torch.zeros((n_loc, 3), dtype=self.dtype, device=self.dev)
-        self.e_atom = torch.zeros(n_loc, dtype=self.dtype, device=self.dev)
+        self.types[:n_own] = types
+        self.vel, self.mass = vel, mass
+        rows = n_loc if self.force_mode == self._lib.FORCE_FULL else n_own  # full mode also writes the ghost rows
+        self.frc = frc
+        self.frc_new = torch.empty((rows, 3), dtype=self.dtype, device=self.dev)
         self.send_buf = torch.empty((dom.n_send, 3), dtype=self.dtype, device=self.dev)
-        if n_ghost or self.world > 1:
-            dom.forward(own["pos"], out=self.pos[n_own:])
-            dom.forward(own["types"], out=self.types[n_own:])
-        self.pos_ref = own["pos"].clone() if self.rebuild_every > 1 else None
+        if self.world > 1:
+            dom.forward(pos, out=self.pos[n_own:])
+            dom.forward(types, out=self.types[n_own:])
+        self.pos_ref = pos.clone() if self.rebuild_every > 1 else None
         self.violated.zero_()
         self.lo, self.hi = 0, n_own  # owned range of the local arrays (bench / diagnostics)
         if self.ws is None or self.ws.max_atoms < n_loc:
@@ -295,7 +363,7 @@ class HaloMD:
 
     def _snapshot(self) -> None:
         n = self.n_own
-        self._snap = (self.pos[:n].clone(), self.vel.clone(), self.frc[:n].clone(), self.steps)
+        self._snap = (self.pos[:n].clone(), self.vel.clone(), self.frc.clone(), self.steps)
 
     # ------------------------------------------------------------------------------ pieces of a step
     def _exchange_positions(self) -> None:
@@ -317,8 +385,9 @@ class HaloMD:
         if self.force_mode == _lib.FORCE_FULL and self.world > 1:
             dom = self.domain
             back = dom.reverse(self.frc_new[self.n_own:])
-            _lib.check(self.lib.pantea_halo_unpack_add(_lib.ptr(self.frc_new), _lib.ptr(back), _lib.ptr(dom.rev_order),
-                                                       _lib.ptr(dom.rev_first), self.n_own, self.code, _lib.stream_ptr()))
+            order, first_ = dom.reverse_index()
+            _lib.check(self.lib.pantea_halo_unpack_add(_lib.ptr(self.frc_new), _lib.ptr(back), _lib.ptr(order),
+                                                       _lib.ptr(first_), self.n_own, self.code, _lib.stream_ptr()))
 
     def _segment_violated(self) -> bool:
         if self.pos_ref is None:
@@ -331,11 +400,16 @@ class HaloMD:
     def _rebuild(self) -> None:
         """Migration + new ghost lists from the current owned positions (host-synchronous)."""
         n = self.n_own
-        arrays = [self.pos[:n], self.vel, self.frc[:n], self.mass, self.types[:n]]
+        if self.rebuild_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        arrays = [self.pos[:n], self.vel, self.frc, self.mass, self.types[:n]]
         (pos, vel, frc, mass, types), self.gid = self.domain.migrate(self.pos[:n], arrays, self.gid)
-        self._install({"pos": pos.contiguous(), "vel": vel.contiguous(), "frc": frc.contiguous(),
-                       "mass": mass.contiguous(), "types": types.contiguous()})
+        self._install(pos, vel, frc, mass, types)
         self._since = 0
+        if self.rebuild_events is not None:
+            ev[1].record()
+            self.rebuild_events.append(ev)
 
     def _advance(self) -> int:
         """One step; returns 0, or the number of steps that were rolled back (a violated ghost-shell skin)."""
@@ -373,7 +447,7 @@ class HaloMD:
         n = self.n_own
         self.pos[:n].copy_(pos)
         self.vel.copy_(vel)
-        self.frc[:n].copy_(frc)
+        self.frc.copy_(frc)
         self.steps = step0
         self.rebuild_every = max(1, self.rebuild_every // 2)
         self._since = self.rebuild_every  # the repeated segment starts with a rebuild
@@ -416,9 +490,10 @@ class HaloMD:
 
     def potential_energy(self) -> torch.Tensor:
         keep = self.frc_new.clone()
-        self._evaluate(e_atom=self.e_atom)
+        e_atom = torch.zeros(self.n_local, dtype=self.dtype, device=self.dev)
+        self._evaluate(e_atom=e_atom)
         self.frc_new.copy_(keep)
-        e = self.e_atom[: self.n_own].double().sum().reshape(1)
+        e = e_atom[: self.n_own].double().sum().reshape(1)
         if self.world > 1:
             dist.all_reduce(e, op=dist.ReduceOp.SUM)
         return e

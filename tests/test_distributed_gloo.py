@@ -120,7 +120,8 @@ def _halo_worker(rank, world, port, dims, out):
             # reverse halo: every ghost row returns 1 -> an owned atom collects its number of ghost copies
             back = dom.reverse(torch.ones((n_ghost, 1), dtype=torch.float64))
             copies = torch.zeros(len(gid), dtype=torch.float64).index_add_(0, dom.send_idx, back[:, 0])
-            occ = (dom.rev_first[1:] - dom.rev_first[:-1]).double()
+            rev_first = dom.reverse_index()[1]
+            occ = (rev_first[1:] - rev_first[:-1]).double()
             res[phase] = (gid.numpy().copy(), own_pos.numpy().copy(), own_vel.numpy().copy(), own_types.numpy().copy(),
                           ghost_gid.numpy().copy(), ghost_pos.numpy().copy(), copies.numpy().copy(),
                           bool(torch.equal(copies, occ)),

@@ -33,8 +33,8 @@ def _workspace(dev_pot, n, dtype=torch.float64, cap=None):
 
 
 # ------------------------------------------------------------------------------------------ brick decomposition
-@pytest.mark.parametrize("n_atoms,world", [(3000, 2), (12000, 4), (12000, 8), (24000, 8)])
-def test_brick_local_evaluation_matches_global(n_atoms, world, pot):
+@pytest.mark.parametrize("n_atoms,world,balanced", [(3000, 2, False), (12000, 4, True), (12000, 8, False), (24000, 8, True)])
+def test_brick_local_evaluation_matches_global(n_atoms, world, balanced, pot):
     from pantea_b200.halo import BrickGrid
     pos, types, box = water_box(n_atoms)
     dev = device_potential_from_specs(pot)
@@ -47,8 +47,11 @@ def test_brick_local_evaluation_matches_global(n_atoms, world, pot):
     _, ea_full, f_full = ws.energy_forces(True, True, True)
     ea_full, f_full = ea_full.cpu().numpy(), f_full.cpu().numpy()
 
-    grid = BrickGrid(list(box), world)
+    grid = BrickGrid.balanced(list(box), world, p) if balanced else BrickGrid(list(box), world)
     owner = grid.owner(p)
+    if balanced:   # boundaries at the atom-count quantiles: the bricks own (almost) the same number of atoms
+        counts = torch.bincount(owner, minlength=world)
+        assert int(counts.max() - counts.min()) <= 0.05 * n_atoms / world + 8
     seen = np.zeros(n_atoms, dtype=int)
     e_sum = 0.0
     for r in range(world):
@@ -163,7 +166,7 @@ def test_full_forces_wide_potential_and_mixed_kinds():
         sfs = [SymFuncSpec(1, "cos", 9.0, 1), SymFuncSpec(2, "tanhu", 12.0, 2, 0, 0.02, 1.5),
                SymFuncSpec(2, "exp", 9.0, 1, 0, 0.05, 0.0), SymFuncSpec(3, "cos", 9.0, 1, 1, 0.01, 0.0, 1.0, 1.5),
                SymFuncSpec(3, "tanhu", 12.0, 1, 2, 0.02, 0.0, 1.0, 3.0), SymFuncSpec(9, "tanh", 12.0, 2, 2, 0.005, 0.0, 1.0, 1.0),
-               SymFuncSpec(9, "hard", 9.0, 1, 2, 0.01, 0.0, -1.0, 2.0)]
+               SymFuncSpec(9, "cos", 9.0, 1, 2, 0.01, 0.0, -1.0, 2.0)]
         n = len(sfs)
         layers = [(rng.uniform(-1, 1, (n, 6)) / 3.0, rng.uniform(-0.1, 0.1, 6), "softplus"),
                   (rng.uniform(-1, 1, (6, 1)), np.zeros(1), "identity")]
