@@ -184,7 +184,8 @@ def test_brick_grid_covers_every_neighbour(world, expect):
     assert grid.dims == expect
     pos = torch.from_numpy(rng.uniform(0.0, 1.0, (n, 3)) * box)
     pos[:8] = torch.tensor([[0.0, 0.0, 0.0], [13.0, 13.0, 13.0], [25.999999999, 0.0, 13.0], [12.999999999, 13.0, 0.0],
-                            [13.0, 0.0, 25.999999999], [6.0, 19.0, 13.0], [19.0, 6.0, 7.0], [7.0, 6.0, 19.0]])
+                            [13.0, 0.0, 25.999999999], [6.0, 19.0, 13.0], [19.0, 6.0, 7.0], [7.0, 6.0, 19.0]],
+                           dtype=torch.float64)
     owner = grid.owner(pos)
     assert owner.min() >= 0 and owner.max() < world
     d = pos[:, None, :] - pos[None, :, :]
