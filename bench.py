@@ -57,8 +57,8 @@ def parse_args():
     ap.add_argument("--halo", default="off", choices=["auto", "on", "off"],
                     help="secondary measurement `halo_exchange`: the same K steps with the brick-decomposed HaloMD "
                          "(ghost-atom exchange); auto = when N > 1 (default off: opt-in)")
-    ap.add_argument("--halo-skin", type=float, default=1.0, help="ghost-shell skin (Bohr) of the halo measurement")
-    ap.add_argument("--halo-every", type=int, default=2, help="ghost lists rebuilt every this many steps")
+    ap.add_argument("--halo-skin", type=float, default=4.4, help="ghost-shell skin (Bohr) of the halo measurement")
+    ap.add_argument("--halo-every", type=int, default=8, help="ghost lists rebuilt every this many steps")
     args = ap.parse_args()
     args.atoms = 3 * (args.atoms // 3)  # whole water molecules: "100 000 atoms" = 33 333 molecules = 99 999 atoms
     return args
