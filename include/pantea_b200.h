@@ -176,6 +176,13 @@ int pantea_md_update_positions(void* positions, const void* velocities, const vo
                                int64_t end, const double* box, double dt, int32_t dtype, void* stream);
 int pantea_md_update_velocities(void* velocities, void* forces /*in: F(t), out: F(t+dt)*/, const void* new_forces,
                                 int64_t begin, int64_t end, double dt, int32_t dtype, void* stream);
+/* Extension ("mass_scaled physical MD"): the same two updates with the acceleration F / m in place of
+   F; masses [n] in the workspace dtype, NULL = the reference update.  With PANTEA_FORCE_FULL forces this is the usual
+   energy-conserving velocity Verlet. */
+int pantea_md_update_positions_mass(void* positions, const void* velocities, const void* forces, const void* masses,
+                                    int64_t begin, int64_t end, const double* box, double dt, int32_t dtype, void* stream);
+int pantea_md_update_velocities_mass(void* velocities, void* forces, const void* new_forces, const void* masses,
+                                     int64_t begin, int64_t end, double dt, int32_t dtype, void* stream);
 /* ke_out: DEVICE double[1] = 0.5 * sum m v^2 over [begin,end) (fixed-order reduction) */
 int pantea_md_kinetic_energy(const void* velocities, const void* masses, int64_t begin, int64_t end, double* ke_out,
                              int32_t dtype, void* stream);
@@ -190,6 +197,8 @@ typedef struct pantea_md_params {
     double kb;        /* Boltzmann constant in the caller's units */
     int32_t record;   /* != 0: write (E_pot, E_kin) of every step into `scalars` */
     int32_t use_graph;/* != 0: replay the step as a CUDA graph */
+    int32_t mass_scaled; /* != 0: extension -- accelerations F/m in both half-steps (the reference integrator has none) */
+    int32_t force_mode;  /* PANTEA_FORCE_REFERENCE (0, the reference) or PANTEA_FORCE_FULL */
 } pantea_md_params;
 
 /* Runs n_steps velocity-Verlet steps entirely on the device, no host synchronisation inside:

@@ -139,8 +139,10 @@ def energy_forces(specs: Sequence[ElementSpec], pos, types, box, want_forces: bo
 
 
 def md_run(specs: Sequence[ElementSpec], pos, vel, mass, types, box, dt: float, n_steps: int,
-           t_target: float = 0.0, tau: float = 0.0, kb: float = 3.166811563e-6):
-    """Returns (pos, vel, forces, scalars[n_steps+1,3] = (Epot, Ekin, T))."""
+           t_target: float = 0.0, tau: float = 0.0, kb: float = 3.166811563e-6, mass_scaled: bool = False):
+    """Returns (pos, vel, forces, scalars[n_steps+1,3] = (Epot, Ekin, T)).  `mass_scaled` (extension, not a reference
+    mode): accelerations F/m in place of F."""
+    lib().orc_set_mass_scaled(C.c_int(1 if mass_scaled else 0))
     pos, types, box = _prep(np.array(pos, copy=True), types, box)
     vel = np.ascontiguousarray(np.array(vel, copy=True), dtype=np.float64)
     mass = np.ascontiguousarray(np.asarray(mass, dtype=np.float64).reshape(-1))
@@ -150,6 +152,7 @@ def md_run(specs: Sequence[ElementSpec], pos, vel, mass, types, box, dt: float, 
     rc = lib().orc_md_run(packed.array, C.c_int(packed.n), _dptr(pos), _dptr(vel), _dptr(forces), _dptr(mass),
                           _iptr(types), C.c_long(len(pos)), _dptr(box), C.c_double(dt), C.c_long(n_steps),
                           C.c_double(t_target), C.c_double(tau), C.c_double(kb), _dptr(scalars))
+    lib().orc_set_mass_scaled(C.c_int(0))
     assert rc == 0
     return pos, vel, forces, scalars
 

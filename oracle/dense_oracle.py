@@ -294,6 +294,28 @@ def energy_and_full_forces(models: Sequence[ElementModel], positions: Tensor, ty
     return total.detach(), -g
 
 
+def md_run_full(models: Sequence[ElementModel], positions: Tensor, velocities: Tensor, masses: Tensor, types: Tensor,
+                box: Optional[Tensor], dt: float, n_steps: int, mass_scaled: bool = True):
+    """Velocity Verlet with the FULL force (and, by default, accelerations F/m): the oracle of the library's
+    `pantea_md_params.{force_mode = FULL, mass_scaled}` extensions -- NOT a reference mode (the reference integrates
+    the central-role force without mass, molecular_dynamics.py:16-30).  Same update order as `verlet_positions` /
+    `verlet_velocities`.  Returns (positions, velocities, forces, scalars [n_steps + 1, 2] = (E_pot, E_kin))."""
+    x, v = positions.clone(), velocities.clone()
+    m = masses.reshape(-1, 1)
+    inv = 1.0 / m if mass_scaled else torch.ones_like(m)
+    e, f = energy_and_full_forces(models, x, types, box)
+    scal = [(float(e), float(kinetic_energy(v, m)))]
+    for _ in range(n_steps):
+        x = x + v * dt + 0.5 * (f * inv) * dt * dt
+        if box is not None:
+            x = wrap_into_box(x, box)
+        e, f_new = energy_and_full_forces(models, x, types, box)
+        v = v + 0.5 * (f * inv + f_new * inv) * dt
+        f = f_new
+        scal.append((float(e), float(kinetic_energy(v, m))))
+    return x, v, f, torch.tensor(scal, dtype=torch.float64)
+
+
 # ----------------------------------------------------------------------------- MD pieces
 def verlet_positions(x: Tensor, v: Tensor, f: Tensor, dt: float) -> Tensor:
     """pantea/simulation/molecular_dynamics.py:16-21 (no mass division)."""

@@ -476,6 +476,11 @@ int orc_energy_forces(const orc_element *els, int n_el, const double *pos, const
 /* scalars_out [n_steps + 1, 3] = (E_pot, E_kin, T) recorded at step 0..n_steps when not NULL.
    tau <= 0 disables the thermostat.  pos/vel/forces are updated in place; forces must hold
    F(pos) on entry (like System.__post_init__, system.py:79-82). */
+/* extension switch (not a reference mode): accelerations F/m instead of F in both half-steps -- the oracle of
+   pantea_md_params.mass_scaled */
+static int g_mass_scaled = 0;
+void orc_set_mass_scaled(int flag) { g_mass_scaled = flag; }
+
 int orc_md_run(const orc_element *els, int n_el, double *pos, double *vel, double *forces, const double *mass,
                const int *types, long n, const double *box, double dt, long n_steps, double t_target, double tau,
                double kb, double *scalars_out) {
@@ -495,10 +500,16 @@ int orc_md_run(const orc_element *els, int n_el, double *pos, double *vel, doubl
             scalars_out[3 * step + 2] = 2.0 * ke / (3.0 * (double)n * kb);
         }
         if (step == n_steps) break;
-        for (long i = 0; i < 3 * n; ++i) pos[i] = pos[i] + vel[i] * dt + 0.5 * forces[i] * dt * dt;
+        if (g_mass_scaled)
+            for (long i = 0; i < 3 * n; ++i) pos[i] = pos[i] + vel[i] * dt + 0.5 * (forces[i] / mass[i / 3]) * dt * dt;
+        else
+            for (long i = 0; i < 3 * n; ++i) pos[i] = pos[i] + vel[i] * dt + 0.5 * forces[i] * dt * dt;
         if (box) orc_wrap(pos, n, box);
         rc |= orc_energy_forces(els, n_el, pos, types, n, box, eat, fnew, NULL);
-        for (long i = 0; i < 3 * n; ++i) vel[i] = vel[i] + 0.5 * (forces[i] + fnew[i]) * dt;
+        if (g_mass_scaled)
+            for (long i = 0; i < 3 * n; ++i) vel[i] = vel[i] + 0.5 * (forces[i] / mass[i / 3] + fnew[i] / mass[i / 3]) * dt;
+        else
+            for (long i = 0; i < 3 * n; ++i) vel[i] = vel[i] + 0.5 * (forces[i] + fnew[i]) * dt;
         memcpy(forces, fnew, sizeof(double) * 3 * (size_t)n);
         if (tau > 0.0) {
             double ke = 0.0;

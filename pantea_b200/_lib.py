@@ -45,7 +45,7 @@ class PotentialDesc(C.Structure):
 
 class MDParams(C.Structure):
     _fields_ = [("dt", C.c_double), ("t_target", C.c_double), ("tau", C.c_double), ("kb", C.c_double),
-                ("record", C.c_int32), ("use_graph", C.c_int32)]
+                ("record", C.c_int32), ("use_graph", C.c_int32), ("mass_scaled", C.c_int32), ("force_mode", C.c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/pantea_b200.h
@@ -70,6 +70,8 @@ PROTOTYPES = {
     "pantea_energy_forces": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP]),
     "pantea_md_update_positions": (C.c_int, [_VP, _VP, _VP, _I64, _I64, C.POINTER(_DBL), _DBL, _I32, _VP]),
     "pantea_md_update_velocities": (C.c_int, [_VP, _VP, _VP, _I64, _I64, _DBL, _I32, _VP]),
+    "pantea_md_update_positions_mass": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I64, C.POINTER(_DBL), _DBL, _I32, _VP]),
+    "pantea_md_update_velocities_mass": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I64, _DBL, _I32, _VP]),
     "pantea_md_kinetic_energy": (C.c_int, [_VP, _VP, _I64, _I64, _VP, _I32, _VP]),
     "pantea_md_rescale_velocities": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _DBL, _DBL, _DBL, _DBL, _I32, _VP]),
     "pantea_md_run": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I64, C.POINTER(_DBL), _I64, C.POINTER(MDParams), _VP, _VP]),

@@ -205,12 +205,12 @@ struct pantea_workspace {
         const void *pos = nullptr, *vel = nullptr, *frc = nullptr, *mass = nullptr, *types = nullptr, *scalars = nullptr;
         int64_t n = 0, epoch = -1;
         double dt = 0, tau = 0, t0 = 0, kb = 0, box[3] = {0, 0, 0};
-        int record = 0, has_box = 0;
+        int record = 0, has_box = 0, mass_scaled = 0, force_mode = 0;
         bool operator==(const GraphKey& o) const {
             return pos == o.pos && vel == o.vel && frc == o.frc && mass == o.mass && types == o.types &&
                    scalars == o.scalars && n == o.n && dt == o.dt && tau == o.tau && t0 == o.t0 && kb == o.kb &&
                    box[0] == o.box[0] && box[1] == o.box[1] && box[2] == o.box[2] && record == o.record &&
-                   has_box == o.has_box && epoch == o.epoch;
+                   has_box == o.has_box && epoch == o.epoch && mass_scaled == o.mass_scaled && force_mode == o.force_mode;
         }
     } md_key;
 };

@@ -29,24 +29,29 @@ struct Box3 {
     int has_box;
 };
 
+// `mass` (nullable) selects the mass-scaled extension: the acceleration F/m takes the place of F (the
+// reference integrator itself carries no mass)
 template <typename T>
 __global__ void md_positions_kernel(T* __restrict__ pos, const T* __restrict__ vel, const T* __restrict__ frc,
-                                    int64_t begin3, int64_t end3, Box3 box, T dt) {
+                                    const T* __restrict__ mass, int64_t begin3, int64_t end3, Box3 box, T dt) {
     int64_t e = begin3 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= end3) return;
+    const T a = mass ? frc[e] / mass[e / 3] : frc[e];
     // x + v*dt + 0.5*F*dt*dt evaluated left to right without contraction (molecular_dynamics.py:20)
-    T x = add_rn(add_rn(pos[e], mul_rn(vel[e], dt)), mul_rn(mul_rn(mul_rn((T)0.5, frc[e]), dt), dt));
+    T x = add_rn(add_rn(pos[e], mul_rn(vel[e], dt)), mul_rn(mul_rn(mul_rn((T)0.5, a), dt), dt));
     if (box.has_box) x = wrap_coord<T>(x, (T)box.l[e % 3]);
     pos[e] = x;
 }
 
 template <typename T>
 __global__ void md_velocities_kernel(T* __restrict__ vel, T* __restrict__ frc, const T* __restrict__ frc_new,
-                                     int64_t begin3, int64_t end3, T dt) {
+                                     const T* __restrict__ mass, int64_t begin3, int64_t end3, T dt) {
     int64_t e = begin3 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= end3) return;
     const T fn = frc_new[e];
-    vel[e] = add_rn(vel[e], mul_rn(mul_rn((T)0.5, add_rn(frc[e], fn)), dt));  // molecular_dynamics.py:30
+    T f0 = frc[e], f1 = fn;
+    if (mass) { const T m = mass[e / 3]; f0 = f0 / m; f1 = f1 / m; }
+    vel[e] = add_rn(vel[e], mul_rn(mul_rn((T)0.5, add_rn(f0, f1)), dt));  // molecular_dynamics.py:30
     frc[e] = fn;
 }
 
@@ -141,37 +146,53 @@ static const int64_t kKeScratchCap = 1 << 17;
 
 extern "C" {
 
-int pantea_md_update_positions(void* positions, const void* velocities, const void* forces, int64_t begin, int64_t end,
-                               const double* box, double dt, int32_t dtype, void* stream) {
+int pantea_md_update_positions_mass(void* positions, const void* velocities, const void* forces, const void* masses,
+                                    int64_t begin, int64_t end, const double* box, double dt, int32_t dtype, void* stream) {
     if (!positions || !velocities || !forces) return fail(PANTEA_EINVAL, "pantea_md_update_positions: NULL argument");
+    if (dtype != PANTEA_F64 && dtype != PANTEA_F32) return fail(PANTEA_EINVAL, "pantea_md_update_positions: dtype must be PANTEA_F64 or PANTEA_F32");
     if (end <= begin) return PANTEA_OK;
     const int64_t n3 = 3 * (end - begin);
     const int blocks = (int)((n3 + 255) / 256);
     Box3 b = make_box(box);
     if (dtype == PANTEA_F64)
         md_positions_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((double*)positions, (const double*)velocities,
-                                                                             (const double*)forces, 3 * begin, 3 * end, b, dt);
+                                                                             (const double*)forces, (const double*)masses,
+                                                                             3 * begin, 3 * end, b, dt);
     else
         md_positions_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)positions, (const float*)velocities,
-                                                                            (const float*)forces, 3 * begin, 3 * end, b, (float)dt);
+                                                                            (const float*)forces, (const float*)masses,
+                                                                            3 * begin, 3 * end, b, (float)dt);
+    PANTEA_LAUNCH_CHECK();
+    return PANTEA_OK;
+}
+
+int pantea_md_update_positions(void* positions, const void* velocities, const void* forces, int64_t begin, int64_t end,
+                               const double* box, double dt, int32_t dtype, void* stream) {
+    return pantea_md_update_positions_mass(positions, velocities, forces, nullptr, begin, end, box, dt, dtype, stream);
+}
+
+int pantea_md_update_velocities_mass(void* velocities, void* forces, const void* new_forces, const void* masses,
+                                     int64_t begin, int64_t end, double dt, int32_t dtype, void* stream) {
+    if (!velocities || !forces || !new_forces) return fail(PANTEA_EINVAL, "pantea_md_update_velocities: NULL argument");
+    if (dtype != PANTEA_F64 && dtype != PANTEA_F32) return fail(PANTEA_EINVAL, "pantea_md_update_velocities: dtype must be PANTEA_F64 or PANTEA_F32");
+    if (end <= begin) return PANTEA_OK;
+    const int64_t n3 = 3 * (end - begin);
+    const int blocks = (int)((n3 + 255) / 256);
+    if (dtype == PANTEA_F64)
+        md_velocities_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((double*)velocities, (double*)forces,
+                                                                              (const double*)new_forces, (const double*)masses,
+                                                                              3 * begin, 3 * end, dt);
+    else
+        md_velocities_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)velocities, (float*)forces,
+                                                                             (const float*)new_forces, (const float*)masses,
+                                                                             3 * begin, 3 * end, (float)dt);
     PANTEA_LAUNCH_CHECK();
     return PANTEA_OK;
 }
 
 int pantea_md_update_velocities(void* velocities, void* forces, const void* new_forces, int64_t begin, int64_t end,
                                 double dt, int32_t dtype, void* stream) {
-    if (!velocities || !forces || !new_forces) return fail(PANTEA_EINVAL, "pantea_md_update_velocities: NULL argument");
-    if (end <= begin) return PANTEA_OK;
-    const int64_t n3 = 3 * (end - begin);
-    const int blocks = (int)((n3 + 255) / 256);
-    if (dtype == PANTEA_F64)
-        md_velocities_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((double*)velocities, (double*)forces,
-                                                                              (const double*)new_forces, 3 * begin, 3 * end, dt);
-    else
-        md_velocities_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)velocities, (float*)forces,
-                                                                             (const float*)new_forces, 3 * begin, 3 * end, (float)dt);
-    PANTEA_LAUNCH_CHECK();
-    return PANTEA_OK;
+    return pantea_md_update_velocities_mass(velocities, forces, new_forces, nullptr, begin, end, dt, dtype, stream);
 }
 
 int pantea_md_kinetic_energy(const void* velocities, const void* masses, int64_t begin, int64_t end, double* ke_out,
@@ -201,14 +222,16 @@ int pantea_md_rescale_velocities(void* velocities, int64_t begin, int64_t end, c
 // one velocity-Verlet step on `st` (reference molecular_dynamics.py:57-77)
 static int md_step(pantea_workspace* ws, void* pos, void* vel, void* frc, const void* mass, const int32_t* types, int64_t n,
                    const double* box, const pantea_md_params* p, double* scalars, cudaStream_t st) {
-    int rc = pantea_md_update_positions(pos, vel, frc, 0, n, box, p->dt, ws->dtype, st);
+    const void* m_int = p->mass_scaled ? mass : nullptr;  // mass-scaled extension (the reference integrator has no mass)
+    int rc = pantea_md_update_positions_mass(pos, vel, frc, m_int, 0, n, box, p->dt, ws->dtype, st);
     if (rc) return rc;
     rc = neighbor_build_impl(ws, pos, types, n, box, nullptr, nullptr, 1, ws->pot->rc_max, st);
     if (rc) return rc;
     const bool record = p->record && scalars;
-    rc = atom_kernel_launch(ws, -1, nullptr, 0, nullptr, nullptr, record ? ws->md_eatom : nullptr, ws->md_forces, st);
+    rc = atom_kernel_launch(ws, -1, nullptr, 0, nullptr, nullptr, record ? ws->md_eatom : nullptr, ws->md_forces, st,
+                            p->force_mode);
     if (rc) return rc;
-    rc = pantea_md_update_velocities(vel, frc, ws->md_forces, 0, n, p->dt, ws->dtype, st);
+    rc = pantea_md_update_velocities_mass(vel, frc, ws->md_forces, m_int, 0, n, p->dt, ws->dtype, st);
     if (rc) return rc;
     const bool thermo = p->tau > 0.0;
     if (thermo || record) {
@@ -242,6 +265,8 @@ int pantea_md_run(pantea_workspace* ws, void* positions, void* velocities, void*
     if (!positions || !velocities || !forces || !masses || !types || !params) return fail(PANTEA_EINVAL, "pantea_md_run: NULL argument");
     if (n_atoms < 1 || n_atoms > ws->max_atoms) return fail(PANTEA_EINVAL, "pantea_md_run: n_atoms out of range");
     if ((n_atoms + kKeChunk - 1) / kKeChunk > ws->e_partial_cap) return fail(PANTEA_EINVAL, "pantea_md_run: too many atoms for the reduction scratch");
+    if (params->force_mode != PANTEA_FORCE_REFERENCE && params->force_mode != PANTEA_FORCE_FULL)
+        return fail(PANTEA_EINVAL, "pantea_md_run: unknown force_mode");
     if (n_steps <= 0) return PANTEA_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool record = params->record && scalars;
@@ -256,6 +281,7 @@ int pantea_md_run(pantea_workspace* ws, void* positions, void* velocities, void*
         key.pos = positions; key.vel = velocities; key.frc = forces; key.mass = masses; key.types = types;
         key.scalars = record ? scalars : nullptr; key.n = n_atoms; key.dt = params->dt; key.tau = params->tau;
         key.t0 = params->t_target; key.kb = params->kb; key.record = record ? 1 : 0; key.has_box = box ? 1 : 0;
+        key.mass_scaled = params->mass_scaled ? 1 : 0; key.force_mode = params->force_mode;
         for (int k = 0; k < 3; ++k) key.box[k] = box ? box[k] : 0.0;
         key.epoch = ws->arg_epoch;  // (after the eager step: its lazy allocations are in)
         if (!(ws->md_graph && key == ws->md_key)) {

@@ -23,9 +23,18 @@ from pantea_b200.units import units
 
 
 class MDSimulator:
-    def __init__(self, time_step: float, thermostat: Optional[BrendsenThermostat] = None) -> None:
+    """`mass_scaled` and `forces` are extensions: `mass_scaled=True` integrates with accelerations F/m,
+    `forces="full"` uses -dE/dr of the total energy; together they give the usual energy-conserving velocity Verlet.
+    The defaults are the reference's integrator (no mass) and force definition (central-role gradient)."""
+
+    def __init__(self, time_step: float, thermostat: Optional[BrendsenThermostat] = None, mass_scaled: bool = False,
+                 forces: str = "reference") -> None:
+        if forces not in ("reference", "full"):
+            raise ValueError(f"Unknown force definition '{forces}'")
         self.time_step: float = float(time_step)
         self.thermostat = thermostat
+        self.mass_scaled = bool(mass_scaled)
+        self.forces = forces
         self.step: int = 0
         self.elapsed_time: float = 0.0
 
@@ -36,21 +45,33 @@ class MDSimulator:
         if self.thermostat is not None:
             system.velocities = self.thermostat.get_rescaled_velocities(self, system)
 
+    def _ensure_forces(self, system: System) -> None:
+        """`System` fills `structure.forces` with the reference force; the full-force extension needs F(t) in its own
+        definition before the first half-kick."""
+        if self.forces == "full" and getattr(system, "_forces_kind", "reference") != "full":
+            system.structure.forces = system.potential.compute_forces(system.structure, forces="full")
+            system._forces_kind = "full"
+
     def verlet_integration(self, system: System) -> None:
         lib = _lib.load()
+        self._ensure_forces(system)
         s = system.structure
         n = s.natoms
         code = _lib.dtype_code(s.dtype)
         pos = s.positions.clone().contiguous()
         vel = system.velocities.clone().contiguous()
         frc = s.forces.clone().contiguous()
-        _lib.check(lib.pantea_md_update_positions(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(frc), 0, n,
-                                                  _lib.box_arg(engine.box_lengths(s)), self.time_step, code,
-                                                  _lib.stream_ptr()))
+        mass = system.masses.reshape(-1).to(s.dtype).contiguous() if self.mass_scaled else None
+        _lib.check(lib.pantea_md_update_positions_mass(_lib.ptr(pos), _lib.ptr(vel), _lib.ptr(frc), _lib.ptr(mass), 0, n,
+                                                       _lib.box_arg(engine.box_lengths(s)), self.time_step, code,
+                                                       _lib.stream_ptr()))
         s.positions = pos
-        new_forces = system.potential.compute_forces(s).contiguous()
-        _lib.check(lib.pantea_md_update_velocities(_lib.ptr(vel), _lib.ptr(frc), _lib.ptr(new_forces), 0, n,
-                                                   self.time_step, code, _lib.stream_ptr()))
+        if self.forces == "full":
+            new_forces = system.potential.compute_forces(s, forces="full").contiguous()
+        else:
+            new_forces = system.potential.compute_forces(s).contiguous()
+        _lib.check(lib.pantea_md_update_velocities_mass(_lib.ptr(vel), _lib.ptr(frc), _lib.ptr(new_forces), _lib.ptr(mass),
+                                                        0, n, self.time_step, code, _lib.stream_ptr()))
         system.velocities = vel
         s.forces = frc  # == new_forces (the kernel rotates F(t+dt) into place)
 
@@ -65,6 +86,7 @@ class MDSimulator:
         if num_steps <= 0:
             return None
         potential._check_scaler_params_exist()
+        self._ensure_forces(system)
         s = system.structure
         dev = potential.device_potential()
         ws = dev.workspace(s.natoms, s.dtype, engine.number_density(s))
@@ -80,7 +102,8 @@ class MDSimulator:
         thermo = self.thermostat
         params = _lib.MDParams(self.time_step, thermo.target_temperature if thermo else 0.0,
                                thermo.time_constant if thermo else 0.0, units.BOLTZMANN_CONSTANT,
-                               1 if record else 0, 1 if use_graph else 0)
+                               1 if record else 0, 1 if use_graph else 0, 1 if self.mass_scaled else 0,
+                               1 if self.forces == "full" else 0)
         _lib.check(_lib.load().pantea_md_run(ws.handle, _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(frc), _lib.ptr(mass),
                                              _lib.ptr(types), s.natoms, _lib.box_arg(box), int(num_steps),
                                              C.byref(params), _lib.ptr(scalars), _lib.stream_ptr()))

@@ -54,6 +54,13 @@ def test_error_convention_without_gpu():
             (lambda: lib.pantea_scaler_stats(stats, 0, 3, 3, 64, stats, None), b"n_rows >= 1"),
             (lambda: lib.pantea_scaler_stats(stats, 4, 3, 2, 64, stats, None), b"n_cols <= ld"),
             (lambda: lib.pantea_lj_energy_forces(None, 1.0, 1.0, None, None, None, None), b"NULL workspace"),
+            (lambda: lib.pantea_halo_pack(None, None, 4, None, None, 0, None, 0.5, None, 64, None), b"NULL array"),
+            (lambda: lib.pantea_halo_pack(None, None, 0, None, None, 0, None, 0.5, None, 16, None), b"dtype"),
+            (lambda: lib.pantea_halo_pack(stats, stats, 0, stats, stats, 4, None, 0.5, None, 64, None), b"needs positions and a flag"),
+            (lambda: lib.pantea_halo_unpack_add(None, None, None, None, 4, 64, None), b"NULL array"),
+            (lambda: lib.pantea_md_update_positions_mass(None, None, None, None, 0, 4, None, 0.25, 64, None), b"NULL argument"),
+            (lambda: lib.pantea_md_update_velocities_mass(stats, stats, stats, None, 0, 4, 0.25, 7, None), b"dtype"),
+            (lambda: lib.pantea_energy_forces(None, None, None, None, 1, None), b"no potential"),
             (lambda: lib.pantea_neighbor_build(None, None, None, 0, None, 1.0, None), b"NULL argument")):
         code = call()
         assert code == _lib.PANTEA_EINVAL and needle in lib.pantea_last_error(), (code, lib.pantea_last_error())

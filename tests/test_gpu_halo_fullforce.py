@@ -217,3 +217,81 @@ def test_compute_forces_full_through_the_public_api(golden_dir):
     assert np.abs(f_full.sum(0)).max() < 1e-13 and np.abs(f_ref.sum(0)).max() > 1e-3   # SURVEY App. C remark
     with pytest.raises(ValueError):
         nnp.compute_forces(s, forces="newton")
+
+
+# ------------------------------------------------------------------------------------------ mass-scaled / full-force MD
+def _md_run_gpu(specs, pos, vel, mass, types, box, dt, n_steps, mass_scaled, force_mode, use_graph=1):
+    import ctypes as C
+    from pantea_b200 import _lib
+    dev = device_potential_from_specs(specs)
+    n = len(pos)
+    ws = _workspace(dev, n)
+    p, v, m, t = cuda(pos), cuda(vel), cuda(mass), cuda(types, torch.int32)
+    ws.bind(p, t, box, dev.r_cutoff)
+    _, _, f = ws.energy_forces(False, True, force_mode=force_mode)
+    scal = torch.zeros((n_steps, 2), dtype=torch.float64, device="cuda")
+    params = _lib.MDParams(dt, 0.0, 0.0, 3.166811563e-6, 1, use_graph, 1 if mass_scaled else 0, force_mode)
+    _lib.check(_lib.load().pantea_md_run(ws.handle, _lib.ptr(p), _lib.ptr(v), _lib.ptr(f), _lib.ptr(m), _lib.ptr(t), n,
+                                         _lib.box_arg(box), n_steps, C.byref(params), _lib.ptr(scal), _lib.stream_ptr()))
+    _lib.check(_lib.load().pantea_neighbor_status(ws.handle, None, _lib.stream_ptr()))
+    return p.cpu().numpy(), v.cpu().numpy(), f.cpu().numpy(), scal.cpu().numpy()
+
+
+@pytest.mark.parametrize("use_graph", [0, 1])
+def test_md_run_mass_scaled_matches_oracle(use_graph, pot):
+    """Integrator extension alone: reference (central-role) forces, accelerations F/m, against the oracle's MD loop."""
+    n_atoms, n_steps, dt = 192, 12, 5.0
+    pos, types, box, vel, mass = _md_arrays(n_atoms)
+    po, vo, fo, sc = c_oracle.md_run(pot, pos, vel, mass, types, box, dt, n_steps, mass_scaled=True)
+    p, v, f, s = _md_run_gpu(pot, pos, vel, mass, types, box, dt, n_steps, True, 0, use_graph)
+    d = p - po
+    d -= np.asarray(box) * np.rint(d / np.asarray(box))
+    assert np.abs(d).max() < 1e-10 and rel_err(v, vo) < 1e-10 and rel_err(f, fo) < 1e-9
+    assert rel_err(s[:, 0], sc[1:, 0]) < 1e-10 and rel_err(s[:, 1], sc[1:, 1]) < 1e-10
+    # and it is a different trajectory than the reference integrator's
+    po_ref, _, _, _ = c_oracle.md_run(pot, pos, vel, mass, types, box, dt, n_steps)
+    assert np.abs(po_ref - po).max() > 1e-3
+
+
+def test_md_full_forces_mass_scaled_follows_dense_oracle_and_conserves_energy(pot):
+    """Full force + F/m = the usual velocity Verlet: parity with the dense autograd oracle, and E_pot + E_kin stays
+    put while both change by ~4 Ha (the reference force is not a gradient of E: with it the same run does not conserve)."""
+    n_atoms, n_steps, dt = 48, 60, 5.0
+    pos, types, box, vel, mass = _md_arrays(n_atoms)
+    models = dense_oracle.models_from_specs(pot)
+    T = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64))  # noqa: E731
+    xo, vo, fo, sc = dense_oracle.md_run_full(models, T(pos), T(vel), T(mass), torch.from_numpy(types), T(box), dt, n_steps)
+    p, v, f, s = _md_run_gpu(pot, pos, vel, mass, types, box, dt, n_steps, True, 1)
+    d = p - xo.numpy()
+    d -= np.asarray(box) * np.rint(d / np.asarray(box))
+    assert np.abs(d).max() < 1e-8 and rel_err(v, vo.numpy()) < 1e-8 and rel_err(f, fo.numpy()) < 1e-7
+    sc = sc.numpy()
+    swing = sc[:, 1].max() - sc[:, 1].min()
+    assert rel_err(s[:, 0], sc[1:, 0]) < 1e-8 and rel_err(s[:, 1], sc[1:, 1]) < 1e-8
+    e_tot = s.sum(1)
+    assert swing > 1.0 and np.abs(e_tot - sc[0].sum()).max() < 5e-3 * swing
+    _, _, _, s_ref = _md_run_gpu(pot, pos, vel, mass, types, box, dt, n_steps, True, 0)
+    assert np.abs(s_ref.sum(1) - sc[0].sum()).max() > 5 * np.abs(e_tot - sc[0].sum()).max()
+
+
+def test_md_simulator_extensions_through_the_public_api(golden_dir):
+    """MDSimulator(mass_scaled=True, forces="full"): the call-by-call path and the device-resident loop agree."""
+    from pantea_b200.atoms import Structure
+    from pantea_b200.potentials import NeuralNetworkPotential
+    from pantea_b200.simulation import MDSimulator, System
+    nnp = NeuralNetworkPotential.from_runner(golden_dir / "h2o.json")
+    nnp.load()
+    pos, types, box = water_box(96)
+    make = lambda: Structure.from_dict({"positions": pos, "elements": ["H" if x == 1 else "O" for x in types],  # noqa: E731
+                                        "lattice": np.diag(box)})
+    a = System.from_structure(make(), nnp, temperature=300.0, seed=3)
+    b = System.from_structure(make(), nnp, temperature=300.0, seed=3)
+    sim_a = MDSimulator(time_step=5.0, mass_scaled=True, forces="full")
+    sim_b = MDSimulator(time_step=5.0, mass_scaled=True, forces="full")
+    for _ in range(6):
+        sim_a.simulate_one_step(a)
+    sim_b.simulate_steps(b, 6)
+    assert (a.positions - b.positions).abs().max() < 1e-10
+    assert (a.velocities - b.velocities).abs().max() < 1e-10 * a.velocities.abs().max() + 1e-15
+    with pytest.raises(ValueError):
+        MDSimulator(time_step=1.0, forces="newton")
