@@ -482,3 +482,62 @@ def test_md_600_steps_energy_curves_follow_oracle(tau, pot):
         scale = np.abs(sc_o[:, col]).max()
         assert np.abs(s[:, col] - sc_o[1:, col]).max() < 1e-7 * scale
     assert sc_o[-1, 1] > 50 * sc_o[0, 1] or tau > 0  # NVE: the kinetic energy really runs away (the test is not vacuous)
+
+
+# ------------------------------------------------------------------------------------------ edge cases
+def test_tiny_structures_and_atoms_without_neighbours(pot):
+    """One atom (with and without a box), two atoms further apart than the cutoff, one water molecule: empty neighbour
+    rows must give the bare network value scale(0) -> MLP, zero forces, and no out-of-range access."""
+    cases = [(np.array([[1.0, 2.0, 3.0]]), np.array([2], dtype=np.int32), np.array([30.0, 30.0, 30.0])),
+             (np.array([[1.0, 2.0, 3.0]]), np.array([1], dtype=np.int32), None),
+             (np.array([[0.0, 0.0, 0.0], [20.0, 0.0, 0.0]]), np.array([1, 2], dtype=np.int32), None),
+             (np.array([[0.0, 0.0, 0.0], [1.43, 1.1, 0.0], [-1.43, 1.1, 0.0]]), np.array([2, 1, 1], dtype=np.int32), None),
+             (np.array([[5.0, 5.0, 5.0], [6.43, 6.1, 5.0], [3.57, 6.1, 5.0]]), np.array([2, 1, 1], dtype=np.int32),
+              np.array([40.0, 41.0, 42.0]))]
+    for pos, types, box in cases:
+        e, ea, f = _energy_forces_gpu(pot, pos, types, box)
+        eo, eao, fo = c_oracle.energy_forces(pot, pos, types, box)
+        assert np.abs(ea - eao).max() < 1e-12 and np.abs(f - fo).max() < 1e-12 and abs(e - eo) < 1e-12
+        e2, _, f2 = _energy_forces_gpu(pot, pos, types, box, torch.float32)
+        assert abs(e2 - eo) < 1e-5 and np.abs(f2 - fo).max() < 1e-5
+
+
+def test_atoms_of_an_element_unknown_to_the_potential(pot):
+    """Types outside 1..n_elements are legal atoms no symmetry function refers to (reference: an element missing from
+    the potential's neighbour lists contributes nothing): zero energy and force for them, and they must not disturb the
+    descriptors of the others."""
+    pos, types, box = water_box(192, seed=6)
+    types = types.copy()
+    types[::7] = 3
+    e, ea, f = _energy_forces_gpu(pot, pos, types, box)
+    eo, eao, fo = c_oracle.energy_forces(pot, pos, types, box)
+    assert rel_err(ea, eao) < FP64_TOL and rel_err(f, fo) < FP64_TOL
+    assert (ea[::7] == 0).all() and (f[::7] == 0).all()
+    dev = device_potential_from_specs(pot)
+    ws = _workspace(dev, len(pos))
+    ws.bind(cuda(pos), cuda(types, torch.int32), box, dev.r_cutoff)
+    for spec in pot:
+        G, dG = ws.acsf(spec.atom_type - 1, len(spec.symfuncs), None, True, True)
+        G_o, dG_o = c_oracle.acsf(spec, pos, types, box)
+        _assert_descriptor_close(G.cpu().numpy(), dG.cpu().numpy(), G_o, dG_o, FP64_TOL)
+    G, dG = ws.acsf(0, len(pot[0].symfuncs), torch.zeros(0, dtype=torch.int32, device="cuda"), True, True)
+    assert G.shape == (0, len(pot[0].symfuncs)) and dG.shape == (0, len(pot[0].symfuncs), 3)   # empty centre list
+
+
+def test_ragged_batch_of_structures(pot):
+    """Dataset preprocessing launch over structures of very different sizes (1 ... 648 atoms, each with its own box)."""
+    sizes = [3, 648, 12, 1 * 3, 192, 81]
+    structs = [water_box(n, seed=40 + i) for i, n in enumerate(sizes)]
+    pos = np.concatenate([s[0] for s in structs])
+    types = np.concatenate([s[1] for s in structs])
+    boxes = np.stack([s[2] for s in structs])
+    ptr = np.concatenate([[0], np.cumsum([len(s[0]) for s in structs])]).astype(np.int32)
+    dev = device_potential_from_specs(pot)
+    ws = _workspace(dev, len(pos), cap=647)
+    ws.bind_batch(cuda(pos), cuda(types, torch.int32), cuda(ptr, torch.int32), cuda(boxes), dev.r_cutoff)
+    for spec in pot:
+        G, dG = ws.acsf(spec.atom_type - 1, len(spec.symfuncs), None, True, True)
+        G, dG = G.cpu().numpy(), dG.cpu().numpy()
+        for s, (p_s, t_s, b_s) in enumerate(structs):
+            G_o, dG_o = c_oracle.acsf(spec, p_s, t_s, b_s)
+            _assert_descriptor_close(G[ptr[s]:ptr[s + 1]], dG[ptr[s]:ptr[s + 1]], G_o, dG_o, FP64_TOL)
