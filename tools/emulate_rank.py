@@ -19,12 +19,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--atoms", type=int, default=100000)
     ap.add_argument("--world", type=int, default=8)
+    ap.add_argument("--all-ranks", action="store_true", help="time every rank's share (load balance), events only")
+    ap.add_argument("--shuffle", action="store_true", help="random atom order: every block is a random sample of the box")
     args = ap.parse_args()
     nnp = NeuralNetworkPotential.from_runner(ROOT / "tests" / "golden" / "h2o.json")
     nnp.load()
     pot = nnp.device_potential()
     pos_h, types_h, box_h = water_box(args.atoms - args.atoms % 3)
     n = len(pos_h)
+    if args.shuffle:
+        perm = np.random.default_rng(0).permutation(n)
+        pos_h, types_h = pos_h[perm], types_h[perm]
     dev = torch.device("cuda")
     pos = torch.as_tensor(pos_h, dtype=torch.float64, device=dev)
     types = torch.as_tensor(types_h, dtype=torch.int32, device=dev)
@@ -37,6 +42,25 @@ def main():
     for _ in range(3):
         ws.bind(pos, types, box, pot.r_cutoff, owned=owned)
         ws.energy_forces(False, True, out_forces=frc)
+    if args.all_ranks:
+        times = []
+        for r in range(args.world):
+            own = (r * per, min(n, (r + 1) * per))
+            for _ in range(2):
+                ws.bind(pos, types, box, pot.r_cutoff, check=False, owned=own)
+                ws.energy_forces(False, True, out_forces=frc)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(10):
+                ws.bind(pos, types, box, pot.r_cutoff, check=False, owned=own)
+                _lib.check(_lib.load().pantea_energy_forces(ws.handle, None, _lib.ptr(frc), None, 0, _lib.stream_ptr()))
+            b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b) / 10)
+        print(f"world={args.world} shuffle={args.shuffle} per-rank build+force ms: " + " ".join(f"{t:.4f}" for t in times)
+              + f" | max {max(times):.4f} mean {sum(times) / len(times):.4f} max/mean {max(times) * len(times) / sum(times):.3f}")
+        return
     from torch.profiler import ProfilerActivity, profile
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 20
