@@ -88,8 +88,8 @@ struct AtomArgs {
 
 template <typename T>
 __host__ __device__ inline size_t eval_smem_bytes(int cap, int n_cls, int n_sf, int n_neurons, int width, int wpa) {
-    size_t t_elems = (size_t)(5 + 2 * n_cls) * cap   // neighbour records
-                     + (size_t)wpa * n_sf * 4;       // per-warp partial sums
+    size_t t_elems = (size_t)(5 + 2 * n_cls) * (cap + 1)  // neighbour records + one all-zero padding record
+                     + (size_t)wpa * n_sf * 4;            // per-warp partial sums
     (void)n_neurons; (void)width;
     return (t_elems * sizeof(T) + 15) & ~size_t(15);
 }
@@ -330,11 +330,16 @@ struct NbrBlock {
 // One angular group (same neighbour types, cutoff and kind), members [m0, m0 + mc), flat over the pair list.
 // FAST: compile-time specialisation for the common RuNNer setting -- G3, tanhu cutoff, integer zeta >= 1 for every member
 // -- whose triplet body is straight-line code; otherwise kind / cutoff / zeta are runtime (warp-uniform) branches.
-template <typename T, int WPA, bool GRAD, int MCH, bool FAST, bool COUNT>
+// LEAN (implies FAST, no counters): additionally zeta == 1 for every member and no minimum image on r_jk; list slots
+// past the end are staged as `pad_entry` = (total, total), the all-zero record behind the atom's last neighbour (u = 0,
+// r = 0, fc = 0, fc'/fc = 0: every term of the triplet body is then exactly zero whatever r_jk evaluates to), so the
+// loop carries no validity mask, no power loop and no wrap branch.
+template <typename T, int WPA, bool GRAD, int MCH, bool FAST, bool COUNT, bool LEAN = false>
 __device__ __forceinline__ void angular_group(const ElementTable& tab, const AngularGroup& grp, int m0, int mc,
                                               const NbrBlock<T>& nb, const int32_t* __restrict__ list, int count,
                                               bool wrap_jk, T lx, T ly, T lz, int lane, int tid_atom, T* my_acc,
-                                              const T* __restrict__ etab, int* stage, unsigned long long& cnt_trip) {
+                                              const T* __restrict__ etab, int* stage, unsigned long long& cnt_trip,
+                                              int pad_entry = 0) {
     constexpr int NU = kNU;
     constexpr int S = 32 * WPA;
     const int ctype = tab.cls[grp.cls].type;
@@ -365,7 +370,14 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
         int* dst = stage + (chunk & 1) * (CH * NU * 32) + lane;
         int e = chunk * (CH * NU * S) + tid_atom;
 #pragma unroll
-        for (int i = 0; i < CH * NU; ++i, e += S) cp_async4(dst + i * 32, list + (e < count ? e : 0));
+        for (int i = 0; i < CH * NU; ++i, e += S) {
+            if (LEAN) {  // the lane reads back only what it wrote itself: a plain store needs no fence here
+                if (e < count) cp_async4(dst + i * 32, list + e);
+                else dst[i * 32] = pad_entry;
+            } else {
+                cp_async4(dst + i * 32, list + (e < count ? e : 0));
+            }
+        }
         cp_async_commit();
     };
     if (n_chunks > 0) stage_chunk(0);
@@ -387,7 +399,7 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
 #pragma unroll
             for (int u = 0; u < NU; ++u) {
                 const int jk = src[u * 32];
-                valid[u] = e0 + u * S < count;
+                valid[u] = LEAN ? true : e0 + u * S < count;
                 const T* pj = nb.rec + (jk & 0xffff) * nb.stride;
                 const T* pk = nb.rec + (jk >> 16) * nb.stride;
                 uxj[u] = pj[0]; uyj[u] = pj[1]; uzj[u] = pj[2]; rj[u] = pj[3]; ivj[u] = pj[4]; fcj[u] = pj[nb.fco];
@@ -397,7 +409,7 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
 #pragma unroll
             for (int u = 0; u < NU; ++u) {  // r_jk = |pbc(d_ij - d_ik)| (reference acsf.py:316-320)
                 T ex = uxj[u] * rj[u] - uxk[u] * rk[u], ey = uyj[u] * rj[u] - uyk[u] * rk[u], ez = uzj[u] * rj[u] - uzk[u] * rk[u];
-                if (wrap_jk) { ex = min_image(ex, lx); ey = min_image(ey, ly); ez = min_image(ez, lz); }
+                if (!LEAN && wrap_jk) { ex = min_image(ex, lx); ey = min_image(ey, ly); ez = min_image(ez, lz); }
                 rjk2[u] = ex * ex + ey * ey + ez * ez;
                 r2[u] = rj[u] * rj[u] + rk[u] * rk[u];
             }
@@ -443,7 +455,7 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
                     for (int u = 0; u < NU; ++u) {
                         const T bs = (T)1 + m_lam[m] * cost[u];
                         T pw1 = (T)1;
-                        if (m_iz[m] != 1)  // warp-uniform; FAST groups only hold integer zeta >= 1
+                        if (!LEAN && m_iz[m] != 1)  // warp-uniform; FAST groups only hold integer zeta >= 1
                             pw1 = (FAST || m_iz[m] > 1) ? powi<T>(bs, m_iz[m] - 1) : pow_general<T>(bs, m_zm1[m]);
                         const T ep = e[u] * fprod[u] * pw1;
                         const T ap = m_pref[m] * bs * ep;  // this triplet's contribution to G
@@ -512,8 +524,8 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
     const int cap = a.scap;
     const size_t per_atom = eval_smem_bytes<T>(cap, a.n_cls_max, a.n_sf_max, a.n_neurons_max, a.width_max, WPA);
     const int stride = 5 + 2 * a.n_cls_max;
-    T* snb = (T*)(smem_raw + (size_t)atom_in_block * per_atom);  // [cap][stride] neighbour records
-    T* sacc = snb + (size_t)stride * cap;                        // [WPA][n_sf_max][4]
+    T* snb = (T*)(smem_raw + (size_t)atom_in_block * per_atom);  // [cap + 1][stride] neighbour records
+    T* sacc = snb + (size_t)stride * (cap + 1);                  // [WPA][n_sf_max][4]
 
     Segments sg;
     sg.load(a.tcount + (size_t)slot * kBuckets, cap);
@@ -561,6 +573,7 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
             }
         }
     }
+    if (tid_atom < stride) snb[(size_t)total * stride + tid_atom] = (T)0;  // padding record of the LEAN triplet loop
     group_sync<WPA>(atom_in_block);
 
     T* my_acc = sacc + (size_t)wrank * a.n_sf_max * 4;
@@ -600,11 +613,19 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
             const int lo = offs[gi], count = offs[gi + 1] - lo;
             NbrBlock<T> nb{snb, stride, 5 + 2 * grp.cls};
             bool fast = tab.cls[grp.cls].type == PANTEA_CUT_TANHU && grp.kind == PANTEA_G3;
-            for (int m = 0; m < grp.count; ++m) fast = fast && tab.members[grp.first + m].izeta >= 1;
+            bool zeta1 = true;
+            for (int m = 0; m < grp.count; ++m) {
+                fast = fast && tab.members[grp.first + m].izeta >= 1;
+                zeta1 = zeta1 && tab.members[grp.first + m].izeta == 1;
+            }
             for (int m0 = 0; m0 < grp.count; m0 += MCH) {
                 const int mc = grp.count - m0 < MCH ? grp.count - m0 : MCH;
                 // the work counters (bench / roofline pass only) are compiled out of the common fast variant
-                if (fast && cnt_trip == ~0ull)
+                if (fast && zeta1 && !wrap_jk && cnt_trip == ~0ull)
+                    angular_group<T, WPA, GRAD, MCH, true, false, true>(tab, grp, m0, mc, nb, lists + lo, count, wrap_jk, lx, ly, lz,
+                                                                        lane, tid_atom, my_acc, s_etab, s_stage[threadIdx.x >> 5], cnt_trip,
+                                                                        total | (total << 16));
+                else if (fast && cnt_trip == ~0ull)
                     angular_group<T, WPA, GRAD, MCH, true, false>(tab, grp, m0, mc, nb, lists + lo, count, wrap_jk, lx, ly, lz,
                                                                   lane, tid_atom, my_acc, s_etab, s_stage[threadIdx.x >> 5], cnt_trip);
                 else if (fast)
