@@ -206,3 +206,52 @@ def test_c_oracle_cell_list_is_bitwise_identical_to_all_pairs(pot):
         c_oracle.set_use_cells(True)
     e1, ea1, f1 = c_oracle.energy_forces(pot, pos, types, box)
     assert np.array_equal(ea0, ea1) and np.array_equal(f0, f1)
+
+
+def test_full_force_oracle_is_the_total_derivative(h2o, pot):
+    """The oracle of the PANTEA_FORCE_FULL extension (autograd through both roles of the dense restatement): zero net
+    force, central differences of the total energy, and the contrast SURVEY.md App. C records for the reference fixture
+    (the full force differs from the reference's central-role force by up to 0.145)."""
+    from oracle import dense_oracle
+    models = dense_oracle.models_from_specs(pot)
+    T = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64))  # noqa: E731
+    pos, types, box = T(h2o["positions"]), torch.from_numpy(h2o["types"]), T(h2o["box"])
+    e, f_full = dense_oracle.energy_and_full_forces(models, pos, types, box)
+    e_c, _, f_central = dense_oracle.energy_and_forces(models, pos, types, box)
+    assert abs(float(e) - float(e_c)) < 1e-15
+    assert f_full.sum(0).abs().max() < 1e-15
+    assert abs(float((f_full - f_central).abs().max()) - 0.145) < 1e-3
+    h = 1e-5
+    for i, c in ((0, 0), (5, 1), (11, 2)):
+        pp, pm = pos.clone(), pos.clone()
+        pp[i, c] += h
+        pm[i, c] -= h
+        ep = dense_oracle.energy_and_forces(models, pp, types, box, want_forces=False)[0]
+        em = dense_oracle.energy_and_forces(models, pm, types, box, want_forces=False)[0]
+        assert abs(float(-(ep - em) / (2 * h)) - float(f_full[i, c])) < 1e-8
+
+
+def test_mass_scaled_full_force_oracle_md_conserves_energy(pot):
+    """Oracle of the `mass_scaled` + full-force MD extension: ordinary velocity Verlet, so E_pot + E_kin is conserved to
+    O(dt^2) while both change by several Ha; the C oracle's mass-scaled loop (reference force) shares the integrator."""
+    from oracle import dense_oracle
+    pos, types, box = water_box(24)
+    vel, mass = md_velocities(types), water_masses(types)
+    models = dense_oracle.models_from_specs(pot)
+    T = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64))  # noqa: E731
+    drift = {}
+    for dt in (2.5, 5.0):
+        _, _, _, sc = dense_oracle.md_run_full(models, T(pos), T(vel), T(mass), torch.from_numpy(types), T(box), dt,
+                                               int(100 / dt))
+        e_tot = sc.sum(1)
+        drift[dt] = float((e_tot - e_tot[0]).abs().max())
+        swing = float(sc[:, 1].max() - sc[:, 1].min())
+        assert swing > 0.1
+    assert drift[5.0] < 5e-3 * swing and drift[2.5] < 0.4 * drift[5.0]   # second-order integrator
+    # integrator arithmetic of the C oracle's mass-scaled loop: one step by hand
+    po, vo, fo, _ = c_oracle.md_run(pot, pos, vel, mass, types, box, 5.0, 1, mass_scaled=True)
+    _, _, f0 = c_oracle.energy_forces(pot, pos, types, box)
+    x1 = np.remainder(pos + vel * 5.0 + 0.5 * (f0 / mass[:, None]) * 25.0, box)
+    np.testing.assert_allclose(po, x1, rtol=0, atol=1e-12)
+    _, _, f1 = c_oracle.energy_forces(pot, x1, types, box)
+    np.testing.assert_allclose(vo, vel + 0.5 * (f0 / mass[:, None] + f1 / mass[:, None]) * 5.0, rtol=1e-12, atol=1e-18)
