@@ -63,5 +63,27 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_ffi_shim() -> Path:
+    """Compile csrc/xla_ffi_shim.cc (XLA FFI handlers over the C ABI) into libpantea_b200_ffi.so.  Needs jaxlib's FFI
+    headers; raises RuntimeError with the reason when they are not available (this image: no jax)."""
+    try:
+        from jax import ffi as jax_ffi
+    except ImportError as exc:
+        raise RuntimeError(f"XLA FFI shim not built: jax.ffi is not importable here ({exc})") from exc
+    lib = build()
+    out = HERE.parent / "libpantea_b200_ffi.so"
+    cmd = [_nvcc(), *ARCH, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", f"-I{ROOT / 'include'}",
+           f"-I{jax_ffi.include_dir()}", str(HERE / "xla_ffi_shim.cc"), "-o", str(out), f"-L{lib.parent}",
+           "-lpantea_b200", f"-Xlinker=-rpath={lib.parent}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        print(res.stdout + res.stderr, file=sys.stderr)
+        raise RuntimeError("XLA FFI shim: compilation failed")
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--ffi" in sys.argv:
+        print(build_ffi_shim())
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

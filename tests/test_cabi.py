@@ -69,3 +69,19 @@ def test_error_convention_without_gpu():
 def test_product_package_never_imports_the_oracle():
     offenders = [p for p in (ROOT / "pantea_b200").rglob("*.py") if re.search(r"^\s*(from|import)\s+oracle\b", p.read_text(), re.M)]
     assert offenders == []
+
+
+def test_xla_ffi_shim_is_optional_and_says_why():
+    """The XLA FFI binding (north star) wraps the same C ABI but needs jaxlib's headers: without jax the shim is not
+    built and the JAX module refuses to import, both with the reason -- never a silent fallback."""
+    import importlib.util
+    shim = (ROOT / "pantea_b200" / "csrc" / "xla_ffi_shim.cc").read_text()
+    for sym in ("pantea_neighbor_build", "pantea_energy_forces", "pantea_acsf_compute", "XLA_FFI_DEFINE_HANDLER_SYMBOL"):
+        assert sym in shim
+    if importlib.util.find_spec("jax") is not None:
+        pytest.skip("jax present: the shim can be built (python -m pantea_b200.csrc.build --ffi)")
+    from pantea_b200.csrc import build
+    with pytest.raises(RuntimeError, match="jax.ffi is not importable"):
+        build.build_ffi_shim()
+    with pytest.raises(ImportError, match="ctypes \\+ torch"):
+        importlib.import_module("pantea_b200.jax_ffi")
