@@ -6,6 +6,8 @@
 // warp-cooperative candidate scan that writes neighbour rows partitioned by neighbour type.
 // The neighbour predicate is evaluated with explicitly rounded, uncontracted arithmetic
 // (r = sqrt((dx*dx + dy*dy) + dz*dz), 0 < r <= rc) so that the sets are bit-identical to the oracle's.
+#include <cstdlib>
+
 #include "internal.cuh"
 #include "math.cuh"
 
@@ -25,6 +27,7 @@ struct BoxArg {
 struct CellArg {
     int nx, ny, nz;
     double inv_x, inv_y, inv_z;  // cells per unit length
+    int r;                       // stencil radius: 1 (cell width > list radius) or 2 (cell width > half the list radius)
 };
 
 __device__ __forceinline__ int bucket_of(int type, int n_types) { return (type >= 1 && type <= n_types) ? type - 1 : n_types; }
@@ -330,7 +333,91 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PANTEA_ROWS_MINBLOCKS) ne
         if (screen) scan_screen(lo, hi); else scan(lo, hi);
     };
 
-    if (MODE == kModeCell) {
+    if (MODE == kModeCell && a.cell.r == 2) {
+        // Half-width cells, 5 x 5 x 5 stencil: 125 (w/2)^3 = 15.6 w^3 of candidate volume instead of 27 w^3.  A (dy, dz)
+        // row of the stencil now holds only ~17 candidates, so the 25 rows are not scanned one by one (half-empty
+        // warps) but as ONE flattened candidate list: lane r < 25 owns row r -- up to two contiguous slot ranges, two
+        // when the x-stencil wraps around the box -- an inclusive warp scan of the range lengths gives every row its
+        // offset, and each 32-wide step finds the row of its candidate by a 5-step search over the lanes' offsets.
+        // Row order (dz outer, dy inner, wrapped x-part first) is the order of the 3 x 3 x 3 scan below.
+        const int nx = a.cell.nx, ny = a.cell.ny, nz = a.cell.nz;
+        const int cx = cell_coord((double)ri.x, a.cell.inv_x, nx);
+        const int cy = cell_coord((double)ri.y, a.cell.inv_y, ny);
+        const int cz = cell_coord((double)ri.z, a.cell.inv_z, nz);
+        int a0 = 0, la = 0, b0 = 0, lb = 0;
+        if (lane < 25) {
+            int z = cz + lane / 5 - 2, y = cy + lane % 5 - 2;
+            z = z < 0 ? z + nz : (z >= nz ? z - nz : z);
+            y = y < 0 ? y + ny : (y >= ny ? y - ny : y);
+            const int rowc = (z * ny + y) * nx;
+            const int xlo = cx - 2, xhi = cx + 2;
+            if (xlo >= 0 && xhi < nx) {
+                a0 = a.cell_start[rowc + xlo]; la = a.cell_start[rowc + xhi + 1] - a0;
+            } else if (xlo < 0) {  // cells xlo + nx .. nx - 1, then 0 .. xhi
+                a0 = a.cell_start[rowc + xlo + nx]; la = a.cell_start[rowc + nx] - a0;
+                b0 = a.cell_start[rowc]; lb = a.cell_start[rowc + xhi + 1] - b0;
+            } else {               // cells xlo .. nx - 1, then 0 .. xhi - nx
+                a0 = a.cell_start[rowc + xlo]; la = a.cell_start[rowc + nx] - a0;
+                b0 = a.cell_start[rowc]; lb = a.cell_start[rowc + xhi - nx + 1] - b0;
+            }
+        }
+        int pe = la + lb;  // inclusive scan over the lanes: end offset of every row in the flattened list
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, pe, o);
+            if (lane >= o) pe += t;
+        }
+        const int ps = pe - (la + lb);
+        const int n_cand = __shfl_sync(kFull, pe, 31);
+        for (int v0 = 0; v0 < n_cand; v0 += 32) {
+            const int v = v0 + lane;
+            int r = 0;  // number of rows that end at or before v == the row of candidate v
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1) {
+                const int pv = __shfl_sync(kFull, pe, (r + st - 1) & 31);
+                if (pv <= v) r += st;
+            }
+            r &= 31;
+            const int off = v - __shfl_sync(kFull, ps, r);
+            const int ra0 = __shfl_sync(kFull, a0, r), rla = __shfl_sync(kFull, la, r), rb0 = __shfl_sync(kFull, b0, r);
+            const int j = off < rla ? ra0 + off : rb0 + (off - rla);
+            const bool has = v < n_cand;
+            bool ok = false;
+            int bucket = 0;
+            if (has) {
+                if (screen) {
+                    const Rec<float> rj = a.rec_screen[j];
+                    float ax = fabsf(rif.x - rj.x), ay = fabsf(rif.y - rj.y), az = fabsf(rif.z - rj.z);
+                    ax = fminf(ax, flx - ax); ay = fminf(ay, fly - ay); az = fminf(az, flz - az);
+                    const float r2f = ax * ax + ay * ay + az * az;
+                    ok = r2f < lo_f;
+                    const bool ambiguous = (ok ? r2f <= a.screen_band : r2f <= hi_f) && j != i;
+                    if (j == i) ok = false;
+                    if (ambiguous) {
+                        const Rec<T> rjx = rec[j];
+                        T dx = sub_rn(ri.x, rjx.x), dy = sub_rn(ri.y, rjx.y), dz = sub_rn(ri.z, rjx.z);
+                        dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz);
+                        const T rr = norm3_rn(dx, dy, dz);
+                        ok = (rr <= rc) && (rr > (T)0);
+                    }
+                    bucket = rec_type(rj);
+                } else {
+                    const Rec<T> rj = rec[j];
+                    T dx = sub_rn(ri.x, rj.x), dy = sub_rn(ri.y, rj.y), dz = sub_rn(ri.z, rj.z);
+                    if (pbc) { dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz); }
+                    const T r2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
+                    if (r2 < rc2_lo) ok = r2 > (T)0;
+                    else if (r2 > rc2_hi) ok = false;
+                    else { const T rr = norm3_rn(dx, dy, dz); ok = (rr <= rc) && (rr > (T)0); }
+                    bucket = rec_type(rj);
+                }
+            }
+            const unsigned m = __ballot_sync(kFull, ok);
+            const int p = cnt + __popc(m & ((1u << lane) - 1u));
+            if (ok && p < a.cap) L[p] = j | (bucket << 28);
+            cnt += __popc(m);
+        }
+    } else if (MODE == kModeCell) {
         int cx = cell_coord((double)ri.x, a.cell.inv_x, a.cell.nx);
         int cy = cell_coord((double)ri.y, a.cell.inv_y, a.cell.ny);
         int cz = cell_coord((double)ri.z, a.cell.inv_z, a.cell.nz);
@@ -513,32 +600,48 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
     ws->n_structs = struct_ptr ? n_structs : 1;
     for (int k = 0; k < 3; ++k) ws->box[k] = box ? box[k] : 0.0;
     BoxArg ba{ws->box[0], ws->box[1], ws->box[2], ws->has_box ? 1 : 0};
-    CellArg ca{1, 1, 1, 0, 0, 0};
+    CellArg ca{1, 1, 1, 0, 0, 0, 1};
 
     bool use_cells = false, use_skin = false;
     if (box && !struct_ptr) {
         // cell width strictly larger than the list radius (relative margin covers the rounding of x * inv); a Verlet
         // skin widens the radius when the box still holds three cells per axis, otherwise it is ignored
         int nc[3];
+        double w_list = 0.0;
         for (int pass = ws->skin > 0.0 ? 0 : 1; pass < 2 && !use_cells; ++pass) {
             const double w = (pass == 0 ? rc + ws->skin : rc) * (1.0 + 1e-7);
             for (int k = 0; k < 3; ++k) nc[k] = (int)std::floor(box[k] / w);
             use_cells = nc[0] >= 3 && nc[1] >= 3 && nc[2] >= 3;
             use_skin = use_cells && pass == 0;
+            w_list = w;
         }
         if (use_skin) rc += ws->skin;
         ws->rc = rc;
         if (use_cells) {
-            // keep the cell count bounded for sparse systems / tiny cutoffs: at most ~4 cells per atom
+            // half-width cells with a 5 x 5 x 5 stencil when the box holds five of them per axis: 42 % less candidate
+            // volume (two atoms closer than the list radius are at most two such cells apart along every axis).
+            // PANTEA_CELL_STENCIL=1 in the environment keeps the 3 x 3 x 3 stencil (diagnostics).
+            static const bool allow_fine = []() { const char* e = std::getenv("PANTEA_CELL_STENCIL"); return !(e && e[0] == '1'); }();
+            int stencil = 1;
+            // the choice follows the SYSTEM size (not a rank's share): the row order, hence every bit of the result,
+            // is then the same on 1 and on N GPUs; small systems keep the coarse grid (fewer cells to scan and sort)
+            if (allow_fine && n >= 2048) {
+                int nf[3];
+                for (int k = 0; k < 3; ++k) nf[k] = (int)std::floor(box[k] / (0.5 * w_list));
+                if (nf[0] >= 5 && nf[1] >= 5 && nf[2] >= 5) { stencil = 2; for (int k = 0; k < 3; ++k) nc[k] = nf[k]; }
+            }
+            const int nc_min = stencil == 2 ? 5 : 3;
+            // keep the cell count bounded for sparse systems / tiny cutoffs: at most ~4 cells per atom (fewer, wider
+            // cells keep the stencil sufficient)
             for (int k = 0; k < 3; ++k) if (nc[k] > 1024) nc[k] = 1024;
             const int64_t max_cells = 4 * n > 64 ? 4 * n : 64;
             while ((int64_t)nc[0] * nc[1] * nc[2] > max_cells) {
                 int big = nc[0] >= nc[1] ? (nc[0] >= nc[2] ? 0 : 2) : (nc[1] >= nc[2] ? 1 : 2);
-                if (nc[big] <= 3) break;
-                nc[big] = nc[big] * 3 / 4 < 3 ? 3 : nc[big] * 3 / 4;
+                if (nc[big] <= nc_min) break;
+                nc[big] = nc[big] * 3 / 4 < nc_min ? nc_min : nc[big] * 3 / 4;
             }
             for (int k = 0; k < 3; ++k) ws->ncell[k] = nc[k];
-            ca = CellArg{nc[0], nc[1], nc[2], nc[0] / box[0], nc[1] / box[1], nc[2] / box[2]};
+            ca = CellArg{nc[0], nc[1], nc[2], nc[0] / box[0], nc[1] / box[1], nc[2] / box[2], stencil};
         }
     }
     // Verlet skin: decide on the device whether this call rebuilds (first call with these atoms / box / cutoff: always)
