@@ -75,10 +75,17 @@ __global__ void cell_scan_kernel(const int32_t* counts, int n, int32_t* start, i
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthreads = blockDim.x;
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += nthreads) {
-        int i = base + tid;
-        int v = i < n ? counts[i] : 0;
-        int x = v;
+    constexpr int K = 8;  // consecutive cells per thread: the half-width grid has ~10x the cells of the coarse one
+    for (int base = 0; base < n; base += nthreads * K) {
+        const int i0 = base + tid * K;
+        int v[K];
+        int x = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            v[k] = i0 + k < n ? counts[i0 + k] : 0;  // all inputs of the thread are read before its outputs are written
+            x += v[k];
+        }
+        const int mine = x;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int y = __shfl_up_sync(kFull, x, o);
@@ -98,9 +105,14 @@ __global__ void cell_scan_kernel(const int32_t* counts, int n, int32_t* start, i
         __syncthreads();
         int carry = carry_s;
         int incl = x + (wid > 0 ? warp_sums[wid - 1] : 0) + carry;
-        if (i < n) {
-            start[i] = incl - v;
-            fill[i] = 0;
+        int run = incl - mine;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (i0 + k < n) {
+                start[i0 + k] = run;
+                fill[i0 + k] = 0;
+            }
+            run += v[k];
         }
         __syncthreads();
         if (tid == nthreads - 1) carry_s = incl;
