@@ -13,4 +13,9 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/ncu_launches.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"hdnnp_eval_kernel|pair_filter_kernel|neighbor_rows_kernel" \
     -s 6 -c 3 -o $out/prof_full -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/ncu_full.log 2>&1
+# neighbour-scan variants of the same build (half-width cells / 5x5x5 stencil against the 3x3x3 scan)
+PANTEA_CELL_STENCIL=1 timeout 200 python bench.py --steps 50 --warmup 3 --no-cpu-baseline > $out/bench_n1_f64_coarse_cells.json 2> /dev/null
+# halo-exchange path on one rank (its N > 1 numbers: torchrun ... bench.py --gpus N --halo on, and tests/mgpu_check.py ... halo)
+timeout 200 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --halo on > $out/bench_n1_halo.json 2> /dev/null
+timeout 100 python tools/halo_probe.py > $out/halo_probe.txt 2>&1
 ls -la $out
