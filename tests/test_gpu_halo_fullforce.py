@@ -214,6 +214,9 @@ def test_compute_forces_full_through_the_public_api(golden_dir):
     types = np.asarray([1 if el == "H" else 2 for el in s.get_elements()], dtype=np.int32)
     _, fo = _full_forces_oracle(specs, frame_pos, types, box)
     assert np.abs(f_full - fo).max() < FP64_TOL * np.abs(fo).max()
+    import json
+    fx = json.loads((golden_dir / "extension_vectors.json").read_text())          # committed known answer
+    assert np.abs(f_full - np.asarray(fx["full_forces"])).max() < FP64_TOL * np.abs(fo).max()
     assert np.abs(f_full.sum(0)).max() < 1e-13 and np.abs(f_ref.sum(0)).max() > 1e-3   # SURVEY App. C remark
     with pytest.raises(ValueError):
         nnp.compute_forces(s, forces="newton")
@@ -295,3 +298,21 @@ def test_md_simulator_extensions_through_the_public_api(golden_dir):
     assert (a.velocities - b.velocities).abs().max() < 1e-10 * a.velocities.abs().max() + 1e-15
     with pytest.raises(ValueError):
         MDSimulator(time_step=1.0, forces="newton")
+
+
+def test_md_full_forces_mass_scaled_matches_the_committed_fixture(golden_dir, pot):
+    """8 velocity-Verlet steps (full force, F/m) of the reference's 12-atom fixture against tests/golden/
+    extension_vectors.json (rc = 12 Bohr > L: every pair has exactly one image, as in the reference)."""
+    import json
+    from oracle.spec import read_runner
+    fx = json.loads((golden_dir / "extension_vectors.json").read_text())["md_full_mass_scaled"]
+    frame = read_runner(golden_dir / "h2o.data")[0]
+    box = frame["box"]
+    pos = np.remainder(frame["positions"], box)
+    p, v, _, s = _md_run_gpu(pot, pos, np.asarray(fx["velocities0"]), np.asarray(fx["masses"]), frame["types"], box,
+                             fx["dt"], fx["n_steps"], True, 1, use_graph=0)
+    d = p - np.asarray(fx["positions"])
+    d -= np.asarray(box) * np.rint(d / np.asarray(box))
+    assert np.abs(d).max() < 1e-9 and rel_err(v, np.asarray(fx["velocities"])) < 1e-8
+    ref = np.asarray(fx["e_pot_e_kin"])[1:]
+    assert rel_err(s[:, 0], ref[:, 0]) < 1e-8 and rel_err(s[:, 1], ref[:, 1]) < 1e-8

@@ -255,3 +255,24 @@ def test_mass_scaled_full_force_oracle_md_conserves_energy(pot):
     np.testing.assert_allclose(po, x1, rtol=0, atol=1e-12)
     _, _, f1 = c_oracle.energy_forces(pot, x1, types, box)
     np.testing.assert_allclose(vo, vel + 0.5 * (f0 / mass[:, None] + f1 / mass[:, None]) * 5.0, rtol=1e-12, atol=1e-18)
+
+
+def test_extension_vectors_fixture_is_reproduced_by_the_oracle(golden_dir, h2o, pot):
+    """tests/golden/extension_vectors.json (made by tests/golden/make_extension_vectors.py) holds the known answers the GPU
+    tests of the full-force / mass-scaled extensions compare with; the oracle must still reproduce it."""
+    from oracle import dense_oracle
+    fx = json.loads((golden_dir / "extension_vectors.json").read_text())
+    models = dense_oracle.models_from_specs(pot)
+    T = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64))  # noqa: E731
+    pos, types, box = T(h2o["positions"]), torch.from_numpy(h2o["types"]), T(h2o["box"])
+    e, f = dense_oracle.energy_and_full_forces(models, pos, types, box)
+    assert abs(float(e) - fx["energy"]) < 1e-15
+    np.testing.assert_allclose(f.numpy(), np.asarray(fx["full_forces"]), rtol=0, atol=1e-14)
+    assert abs(fx["max_abs_difference_to_reference_force"] - 0.145) < 1e-3          # SURVEY.md Appendix C
+    md = fx["md_full_mass_scaled"]
+    x, v, _, sc = dense_oracle.md_run_full(models, pos, T(md["velocities0"]), T(md["masses"]), types, box, md["dt"],
+                                           md["n_steps"])
+    np.testing.assert_allclose(x.numpy(), np.asarray(md["positions"]), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(v.numpy(), np.asarray(md["velocities"]), rtol=1e-10, atol=1e-16)
+    e_tot = np.asarray(md["e_pot_e_kin"]).sum(1)
+    assert np.abs(e_tot - e_tot[0]).max() < 1e-4 and np.ptp(np.asarray(md["e_pot_e_kin"])[:, 1]) > 0.03
