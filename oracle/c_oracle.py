@@ -138,6 +138,18 @@ def energy_forces(specs: Sequence[ElementSpec], pos, types, box, want_forces: bo
     return float(e_atom[begin:end].sum()), e_atom, forces
 
 
+def energy_full_forces(specs: Sequence[ElementSpec], pos, types, box):
+    """(E, e_atom [n], F [n,3]) with the FULL force -dE/dr (extension, not a reference mode; analytic, any size)."""
+    pos, types, box = _prep(pos, types, box)
+    packed = PackedPotential(specs)
+    n = len(pos)
+    e_atom, forces, e_total = np.zeros(n), np.zeros((n, 3)), C.c_double(0.0)
+    rc = lib().orc_energy_full_forces(packed.array, C.c_int(packed.n), _dptr(pos), _iptr(types), C.c_long(n), _dptr(box),
+                                      _dptr(e_atom), _dptr(forces), C.byref(e_total))
+    assert rc == 0
+    return float(e_total.value), e_atom, forces
+
+
 def md_run(specs: Sequence[ElementSpec], pos, vel, mass, types, box, dt: float, n_steps: int,
            t_target: float = 0.0, tau: float = 0.0, kb: float = 3.166811563e-6, mass_scaled: bool = False):
     """Returns (pos, vel, forces, scalars[n_steps+1,3] = (Epot, Ekin, T)).  `mass_scaled` (extension, not a reference

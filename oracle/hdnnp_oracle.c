@@ -472,6 +472,135 @@ int orc_energy_forces(const orc_element *els, int n_el, const double *pos, const
     return rc;
 }
 
+/* ---- full force (extension, NOT a reference mode): F = -dE/dr through both roles ------------------------
+   The oracle of PANTEA_FORCE_FULL at sizes the dense autograd restatement cannot reach; itself checked against
+   that restatement in tests/test_oracle_golden.py.  With w_s = dE_i/dG_is, centre i contributes
+   g_in = sum_s w_s dG_is/d(d_in) to itself (F_i -= g_in) and to neighbour n (F_n += g_in); for a G3 triplet
+      dT/dd_ij = T_c (u_k - c u_j)/r_j + T_j u_j + T_jk u_jk,
+                            dT/dd_ik = T_c (u_j - c u_k)/r_k + T_k u_k - T_jk u_jk.
+   fi[3] accumulates -sum_n g_in, fn[nn][3] the g_in per neighbour. */
+static void acsf_scatter_one(const orc_element *el, const orc_nbr *nb, int nn, const double *box, const double *w,
+                             double *fi, double *fn, double *scratch /* >= 2*nn doubles */) {
+    double *fcn = scratch, *dfcn = scratch + nn;
+    for (int a = 0; a < 3 * nn; ++a) fn[a] = 0.0;
+    for (int s = 0; s < el->n_sf; ++s) {
+        const orc_symfunc *sf = &el->sf[s];
+        if (sf->kind == 1 || sf->kind == 2) {
+            for (int a = 0; a < nn; ++a) {
+                if (nb[a].type != sf->type_j) continue;
+                double r = nb[a].r, fc, dfc, dval;
+                cutoff_fn(sf->cutoff_type, r, sf->r_cutoff, &fc, &dfc);
+                if (sf->kind == 1) dval = dfc;
+                else {
+                    double dr = r - sf->r_shift, ex = exp(-sf->eta * dr * dr);
+                    dval = ex * (dfc - 2.0 * sf->eta * dr * fc);
+                }
+                double c = w[s] * dval / r;
+                fn[3 * a] += c * nb[a].dx; fn[3 * a + 1] += c * nb[a].dy; fn[3 * a + 2] += c * nb[a].dz;
+            }
+            continue;
+        }
+        const int same = sf->type_j == sf->type_k;
+        const double pref = pow(2.0, 1.0 - sf->zeta), lam = sf->lambda0, zeta = sf->zeta, eta = sf->eta;
+        for (int a = 0; a < nn; ++a) cutoff_fn(sf->cutoff_type, nb[a].r, sf->r_cutoff, &fcn[a], &dfcn[a]);
+        for (int a = 0; a < nn; ++a) {
+            if (nb[a].type != sf->type_j) continue;
+            double rj = nb[a].r, fcj = fcn[a], dfcj = dfcn[a];
+            if (fcj == 0.0 && dfcj == 0.0) continue;
+            for (int b = (same ? a + 1 : 0); b < nn; ++b) {
+                if (nb[b].type != sf->type_k) continue;
+                double rk = nb[b].r, fck = fcn[b], dfck = dfcn[b];
+                if (fck == 0.0 && dfck == 0.0) continue;
+                double ex = nb[a].dx - nb[b].dx, ey = nb[a].dy - nb[b].dy, ez = nb[a].dz - nb[b].dz;
+                if (box) { ex = min_image(ex, box[0]); ey = min_image(ey, box[1]); ez = min_image(ez, box[2]); }
+                double rjk = norm3(ex, ey, ez);
+                if (!(rjk > 0.0)) continue; /* acsf.py:325 */
+                double fcjk = 1.0, dfcjk = 0.0, r2 = rj * rj + rk * rk;
+                if (sf->kind == 3) {
+                    cutoff_fn(sf->cutoff_type, rjk, sf->r_cutoff, &fcjk, &dfcjk);
+                    if (fcjk == 0.0 && dfcjk == 0.0) continue;
+                    r2 += rjk * rjk;
+                }
+                double cost = (nb[a].dx * nb[b].dx + nb[a].dy * nb[b].dy + nb[a].dz * nb[b].dz) / (rj * rk);
+                double base = 1.0 + lam * cost;
+                double pw1 = ipow_or_pow(base, zeta - 1.0);
+                double ang = pref * pw1 * base, e = exp(-eta * r2);
+                double Tc = w[s] * pref * zeta * lam * pw1 * e * fcj * fck * fcjk;
+                double Tj = w[s] * ang * e * fck * fcjk * (dfcj - 2.0 * eta * rj * fcj);
+                double Tk = w[s] * ang * e * fcj * fcjk * (dfck - 2.0 * eta * rk * fck);
+                double Tjk = sf->kind == 3 ? w[s] * ang * e * fcj * fck * (dfcjk - 2.0 * eta * rjk * fcjk) : 0.0;
+                double a1 = (Tj - Tc * cost / rj) / rj, a2 = Tc / (rj * rk), a3 = Tjk / rjk;
+                double b1 = (Tk - Tc * cost / rk) / rk;
+                double gjx = a1 * nb[a].dx + a2 * nb[b].dx + a3 * ex, gjy = a1 * nb[a].dy + a2 * nb[b].dy + a3 * ey,
+                       gjz = a1 * nb[a].dz + a2 * nb[b].dz + a3 * ez;
+                double gkx = b1 * nb[b].dx + a2 * nb[a].dx - a3 * ex, gky = b1 * nb[b].dy + a2 * nb[a].dy - a3 * ey,
+                       gkz = b1 * nb[b].dz + a2 * nb[a].dz - a3 * ez;
+                fn[3 * a] += gjx; fn[3 * a + 1] += gjy; fn[3 * a + 2] += gjz;
+                fn[3 * b] += gkx; fn[3 * b + 1] += gky; fn[3 * b + 2] += gkz;
+            }
+        }
+    }
+    fi[0] = fi[1] = fi[2] = 0.0;
+    for (int a = 0; a < nn; ++a) { fi[0] -= fn[3 * a]; fi[1] -= fn[3 * a + 1]; fi[2] -= fn[3 * a + 2]; }
+}
+
+/* e_atom [n], forces [n,3] (full force), e_total; thread-private force arrays summed in thread order */
+int orc_energy_full_forces(const orc_element *els, int n_el, const double *pos, const int *types, long n,
+                           const double *box, double *e_atom, double *forces, double *e_total) {
+    double rc = 0.0;
+    for (int e = 0; e < n_el; ++e) { double r = max_cutoff(&els[e]); if (r > rc) rc = r; }
+    int err = 0;
+    orc_cells cells;
+    orc_cells_build(&cells, pos, n, box, rc);
+    int n_threads = 1;
+#ifdef _OPENMP
+    n_threads = omp_get_max_threads();
+#endif
+    double *priv = (double *)calloc((size_t)n_threads * 3 * (size_t)(n > 0 ? n : 1), sizeof(double));
+#pragma omp parallel num_threads(n_threads)
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        double *mine = priv + (size_t)tid * 3 * (size_t)n;
+        orc_nbr *nb = (orc_nbr *)malloc(sizeof(orc_nbr) * (size_t)(n > 0 ? n : 1));
+        double *scratch = (double *)malloc(sizeof(double) * 2 * (size_t)(n > 0 ? n : 1));
+        double *fn = (double *)malloc(sizeof(double) * 3 * (size_t)(n > 0 ? n : 1));
+        double G[ORC_MAX_SF], w[ORC_MAX_SF];
+#pragma omp for schedule(static)
+        for (long i = 0; i < n; ++i) {
+            const orc_element *el = find_element(els, n_el, types[i]);
+            double E = 0.0;
+            if (el && el->n_sf <= ORC_MAX_SF && el->n_layers > 0) {
+                int nn = cells.active ? gather_neighbors_cells(&cells, pos + 3 * i, pos, types, box, rc, nb, (int)n)
+                                      : gather_neighbors(pos + 3 * i, pos, types, n, box, rc, nb, (int)n);
+                acsf_one(el, nb, nn, box, G, NULL, scratch);
+                if (mlp_one(el, G, &E, w) != 0) err = -1;
+                double fi[3];
+                acsf_scatter_one(el, nb, nn, box, w, fi, fn, scratch);
+                mine[3 * i] += fi[0]; mine[3 * i + 1] += fi[1]; mine[3 * i + 2] += fi[2];
+                for (int a = 0; a < nn; ++a) {
+                    const long j = nb[a].idx;
+                    mine[3 * j] += fn[3 * a]; mine[3 * j + 1] += fn[3 * a + 1]; mine[3 * j + 2] += fn[3 * a + 2];
+                }
+            }
+            if (e_atom) e_atom[i] = E;
+        }
+        free(nb); free(scratch); free(fn);
+    }
+    if (forces)
+        for (long k = 0; k < 3 * n; ++k) {
+            double t = 0.0;
+            for (int th = 0; th < n_threads; ++th) t += priv[(size_t)th * 3 * (size_t)n + k];
+            forces[k] = t;
+        }
+    free(priv);
+    orc_cells_free(&cells);
+    if (e_total && e_atom) { double t = 0.0; for (long i = 0; i < n; ++i) t += e_atom[i]; *e_total = t; }
+    return err;
+}
+
 /* ---- MD driver: velocity Verlet without mass, optional Berendsen --------------------- */
 /* scalars_out [n_steps + 1, 3] = (E_pot, E_kin, T) recorded at step 0..n_steps when not NULL.
    tau <= 0 disables the thermostat.  pos/vel/forces are updated in place; forces must hold

@@ -316,3 +316,14 @@ def test_md_full_forces_mass_scaled_matches_the_committed_fixture(golden_dir, po
     assert np.abs(d).max() < 1e-9 and rel_err(v, np.asarray(fx["velocities"])) < 1e-8
     ref = np.asarray(fx["e_pot_e_kin"])[1:]
     assert rel_err(s[:, 0], ref[:, 0]) < 1e-8 and rel_err(s[:, 1], ref[:, 1]) < 1e-8
+
+
+@pytest.mark.parametrize("n_atoms", [3000, 12000])
+def test_full_forces_match_the_analytic_oracle_at_size(n_atoms, pot):
+    """Cell-list sizes (3x3x3 and 5x5x5 stencils, one and four warps per atom): CUDA full forces against the C oracle's
+    analytic full force, itself checked against the autograd oracle on CPU (tests/test_oracle_golden.py)."""
+    pos, types, box = water_box(n_atoms)
+    e, ea, f = _full_forces_gpu(pot, pos, types, box)
+    eo, eao, fo = c_oracle.energy_full_forces(pot, pos, types, box)
+    assert rel_err(ea, eao) < FP64_TOL and abs(e - eo) < FP64_TOL * np.abs(eao).sum()
+    assert np.abs(f - fo).max() < FP64_TOL * np.abs(fo).max()

@@ -276,3 +276,18 @@ def test_extension_vectors_fixture_is_reproduced_by_the_oracle(golden_dir, h2o, 
     np.testing.assert_allclose(v.numpy(), np.asarray(md["velocities"]), rtol=1e-10, atol=1e-16)
     e_tot = np.asarray(md["e_pot_e_kin"]).sum(1)
     assert np.abs(e_tot - e_tot[0]).max() < 1e-4 and np.ptp(np.asarray(md["e_pot_e_kin"])[:, 1]) > 0.03
+
+
+@pytest.mark.parametrize("case", ["h2o_box", "h2o_open", "wide"])
+def test_c_oracle_full_forces_match_dense_autograd(case, pot):
+    """Tier 2 of the full-force extension oracle (analytic, any size) against tier 1 (autograd through both roles)."""
+    from oracle import dense_oracle
+    specs, n, use_box = {"h2o_box": (pot, 96, True), "h2o_open": (pot, 81, False), "wide": (rune_width_potential(), 48, True)}[case]
+    pos, types, box = water_box(n, seed=4)
+    T = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64))  # noqa: E731
+    e, _, f = c_oracle.energy_full_forces(specs, pos, types, box if use_box else None)
+    eo, fo = dense_oracle.energy_and_full_forces(dense_oracle.models_from_specs(specs), T(pos), torch.from_numpy(types),
+                                                 T(box) if use_box else None)
+    assert abs(e - float(eo)) < 1e-12 * max(1.0, abs(float(eo)))
+    assert np.abs(f - fo.numpy()).max() < 1e-12 * np.abs(fo.numpy()).max()
+    assert np.abs(f.sum(0)).max() < 1e-13
