@@ -10,7 +10,7 @@ import torch
 
 from oracle import c_oracle, dense_oracle as D
 from oracle.spec import (ElementSpec, SymFuncSpec, load_potential, md_velocities, read_runner, rune_width_potential,
-                         type_map, water_box, water_masses, FROM_ATOMIC_MASS, MASS_U)
+                         type_map, water_box, water_masses, FROM_ATOMIC_MASS, KB, MASS_U)
 
 
 @pytest.fixture(scope="module")
@@ -291,3 +291,17 @@ def test_c_oracle_full_forces_match_dense_autograd(case, pot):
     assert abs(e - float(eo)) < 1e-12 * max(1.0, abs(float(eo)))
     assert np.abs(f - fo.numpy()).max() < 1e-12 * np.abs(fo.numpy()).max()
     assert np.abs(f.sum(0)).max() < 1e-13
+
+
+def test_md10k_fixture_head_is_reproduced_by_the_oracle(golden_dir, pot):
+    """tests/golden/md10k_nve_192.json (10 000-step NVE curve of the C oracle, ~1 min to regenerate): its first 500 steps
+    are recomputed here; the rest is trusted to the committed generating script."""
+    fx = json.loads((golden_dir / "md10k_nve_192.json").read_text())
+    pos, types, box = water_box(fx["n_atoms"])
+    vel, mass = md_velocities(types), water_masses(types)
+    _, _, _, sc = c_oracle.md_run(pot, pos, vel, mass, types, box, fx["dt"], 500, 300.0, 0.0, KB)
+    ref = np.asarray(fx["e_pot_e_kin"])
+    assert fx["steps"][:3] == [0, 250, 500]
+    np.testing.assert_allclose(sc[[0, 250, 500], :2], ref[:3], rtol=1e-9)
+    assert fx["spread"]["max_abs_log_ratio_e_kin"] < 0.2 and fx["spread"]["max_rel_dev_first_500_steps"] < 1e-8
+    assert ref[-1, 1] > 1e6 * ref[0, 1]
