@@ -299,31 +299,3 @@ def test_md_simulator_extensions_through_the_public_api(golden_dir):
     with pytest.raises(ValueError):
         MDSimulator(time_step=1.0, forces="newton")
 
-
-def test_md_full_forces_mass_scaled_matches_the_committed_fixture(golden_dir, pot):
-    """8 velocity-Verlet steps (full force, F/m) of the reference's 12-atom fixture against tests/golden/
-    extension_vectors.json (rc = 12 Bohr > L: every pair has exactly one image, as in the reference)."""
-    import json
-    from oracle.spec import read_runner
-    fx = json.loads((golden_dir / "extension_vectors.json").read_text())["md_full_mass_scaled"]
-    frame = read_runner(golden_dir / "h2o.data")[0]
-    box = frame["box"]
-    pos = np.remainder(frame["positions"], box)
-    p, v, _, s = _md_run_gpu(pot, pos, np.asarray(fx["velocities0"]), np.asarray(fx["masses"]), frame["types"], box,
-                             fx["dt"], fx["n_steps"], True, 1, use_graph=0)
-    d = p - np.asarray(fx["positions"])
-    d -= np.asarray(box) * np.rint(d / np.asarray(box))
-    assert np.abs(d).max() < 1e-9 and rel_err(v, np.asarray(fx["velocities"])) < 1e-8
-    ref = np.asarray(fx["e_pot_e_kin"])[1:]
-    assert rel_err(s[:, 0], ref[:, 0]) < 1e-8 and rel_err(s[:, 1], ref[:, 1]) < 1e-8
-
-
-@pytest.mark.parametrize("n_atoms", [3000, 12000])
-def test_full_forces_match_the_analytic_oracle_at_size(n_atoms, pot):
-    """Cell-list sizes (3x3x3 and 5x5x5 stencils, one and four warps per atom): CUDA full forces against the C oracle's
-    analytic full force, itself checked against the autograd oracle on CPU (tests/test_oracle_golden.py)."""
-    pos, types, box = water_box(n_atoms)
-    e, ea, f = _full_forces_gpu(pot, pos, types, box)
-    eo, eao, fo = c_oracle.energy_full_forces(pot, pos, types, box)
-    assert rel_err(ea, eao) < FP64_TOL and abs(e - eo) < FP64_TOL * np.abs(eao).sum()
-    assert np.abs(f - fo).max() < FP64_TOL * np.abs(fo).max()

@@ -542,46 +542,3 @@ def test_ragged_batch_of_structures(pot):
             G_o, dG_o = c_oracle.acsf(spec, p_s, t_s, b_s)
             _assert_descriptor_close(G[ptr[s]:ptr[s + 1]], dG[ptr[s]:ptr[s + 1]], G_o, dG_o, FP64_TOL)
 
-
-def test_md_10k_steps_nve_energy_drift_statistics_follow_oracle(golden_dir, pot):
-    """North star: "NVE energy drift must match the reference over 10k steps".  The mass-less dynamics decorrelates from
-    a 1e-13 perturbation within ~2 000 steps (tests/golden/make_md10k_curve.py measures it), so beyond the first few
-    hundred steps only the statistics of the drift can agree between two correct implementations: against the oracle's
-    10 000-step curve (tests/golden/md10k_nve_192.json, sampled every 250 steps) the CUDA-graph MD loop must match to
-    1e-6 of the energy scale up to step 500 and stay within |log(E_kin / E_kin_oracle)| < 0.4, |dE_pot| < 30 Ha afterwards
-    (five perturbed oracle runs spread by 0.16 and 13 Ha; E_kin grows by seven orders of magnitude along the run)."""
-    import ctypes as C
-    from pantea_b200 import _lib
-    fx = json.loads((golden_dir / "md10k_nve_192.json").read_text())
-    n_atoms, n_steps, dt = fx["n_atoms"], fx["n_steps"], fx["dt"]
-    steps, ref = np.asarray(fx["steps"]), np.asarray(fx["e_pot_e_kin"])
-    pos, types, box = water_box(n_atoms)
-    vel, mass = md_velocities(types), water_masses(types)
-    dev = device_potential_from_specs(pot)
-    ws = _workspace(dev, n_atoms, cap=n_atoms - 1)
-    t, m = cuda(types, torch.int32), cuda(mass)
-    scal = torch.zeros((n_steps, 2), dtype=torch.float64, device="cuda")
-    params = _lib.MDParams(dt, 0.0, 0.0, KB, 1, 1)
-    reports = []
-    for _ in range(8):  # the box densifies along the run: repeat until the capacities have been raised far enough
-        p, v = cuda(pos), cuda(vel)
-        ws.bind(p, t, box, dev.r_cutoff)
-        _, _, f = ws.energy_forces(False, True)
-        _lib.check(_lib.load().pantea_md_run(ws.handle, _lib.ptr(p), _lib.ptr(v), _lib.ptr(f), _lib.ptr(m), _lib.ptr(t), n_atoms,
-                                             _lib.box_arg(box), n_steps, C.byref(params), _lib.ptr(scal), _lib.stream_ptr()))
-        code = _lib.load().pantea_neighbor_status(ws.handle, None, _lib.stream_ptr())
-        if code != _lib.PANTEA_ECAPACITY:
-            _lib.check(code)
-            break
-        reports.append(_lib.load().pantea_last_error().decode())
-    else:
-        raise AssertionError(f"capacities did not settle: {reports}")
-    s = scal.cpu().numpy()
-    assert np.isfinite(s).all()
-    for k, (e_pot, e_kin) in zip(steps[1:], ref[1:]):      # scal[k - 1] holds the energies after step k
-        g_pot, g_kin = s[k - 1]
-        if k <= 500:
-            assert abs(g_pot - e_pot) < 1e-6 * np.abs(ref[:3, 0]).max() and abs(g_kin - e_kin) < 1e-6 * ref[:3, 1].max()
-        else:
-            assert abs(np.log(g_kin / e_kin)) < 0.4 and abs(g_pot - e_pot) < 30.0, (int(k), g_pot, e_pot, g_kin, e_kin)
-    assert s[-1, 1] > 1e6 * ref[0, 1]                      # the kinetic energy really runs away (not vacuous)
