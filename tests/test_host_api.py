@@ -224,3 +224,30 @@ def test_units_and_dtype_switch():
         assert Structure.from_dict(H2O).dtype == torch.float32
     finally:
         default_dtype.FLOATX = old
+
+
+def test_extension_switches_are_validated_on_the_host():
+    """The extensions beyond the reference are opt-in and validated before any device work: unknown force definitions
+    are rejected, HaloMD refuses to run without the CUDA library / a device (no CPU fallback), brick grids reject
+    inconsistent layouts."""
+    import pytest
+    from pantea_b200.halo import BrickGrid, HaloMD, brick_dims
+    from pantea_b200.simulation import MDSimulator
+    sim = MDSimulator(time_step=0.5)
+    assert sim.mass_scaled is False and sim.forces == "reference"          # defaults = the reference's integrator
+    assert MDSimulator(0.5, mass_scaled=True, forces="full").forces == "full"
+    with pytest.raises(ValueError):
+        MDSimulator(0.5, forces="newton")
+    assert brick_dims(8, [10.0, 10.0, 10.0]) == (2, 2, 2) and brick_dims(4, [10.0, 10.0, 40.0]) == (1, 1, 4)
+    with pytest.raises(ValueError):
+        BrickGrid([10.0, 10.0, 10.0], 8, dims=(2, 2, 1))
+    with pytest.raises(ValueError):
+        BrickGrid([10.0, 10.0, 10.0], 2, dims=(2, 1, 1), cuts=[[7.0, 3.0], [], []])
+    grid = BrickGrid([10.0, 10.0, 10.0], 2, dims=(2, 1, 1), cuts=[[4.0], [], []])
+    assert grid.bounds(0) == ([0.0, 0.0, 0.0], [4.0, 10.0, 10.0]) and grid.bounds(1)[0][0] == 4.0
+    pos = torch.tensor([[3.999, 1.0, 1.0], [4.0, 1.0, 1.0], [9.999, 9.0, 9.0], [10.0, 0.0, 0.0]], dtype=torch.float64)
+    assert grid.owner(pos).tolist() == [0, 1, 1, 0]                         # x == L wraps onto the first brick
+    if not torch.cuda.is_available():
+        z = torch.zeros((3, 3), dtype=torch.float64)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            HaloMD(None, z, z, torch.ones(3, dtype=torch.float64), torch.ones(3, dtype=torch.int32), [10.0] * 3, 0.25)
