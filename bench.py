@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--atoms", type=int, default=int(os.environ.get("PANTEA_BENCH_ATOMS", "100000")))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="diagnostics only: skip the oracle comparison before timing")
     ap.add_argument("--skin", type=float, default=0.0,
                     help="Verlet skin (Bohr) of the secondary measurement `verlet_skin`; 0 skips it")
     ap.add_argument("--kernel-times", action="store_true",
@@ -80,7 +81,7 @@ class ClockSampler:
         self.index = device_index
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(device_index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(device_index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -108,6 +109,69 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_cpus() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def pin_oracle_threads(c_oracle) -> int:
+    """The CPU arm always uses every host core it may run on (or PANTEA_REF_THREADS): torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would otherwise decide the CPU number at N > 1."""
+    want = int(os.environ.get("PANTEA_REF_THREADS", "0")) or host_cpus()
+    c_oracle.set_num_threads(want)
+    return c_oracle.num_threads()
+
+
+def parity_check(md, lib, _lib, pos_h, types_h, box_h, dtype, rank, world, dev):
+    """Forces and neighbour counts of the initial state, all atoms, against the CPU oracle (rank 0 compares; the owned
+    rows of every rank are gathered first).  Criterion per force component: |dF| <= rtol * (|F_oracle| + rms(F_oracle)),
+    rtol = 1e-10 (FP64) / 1e-5 (FP32) -- element-wise with an absolute floor at rtol * rms, because single components
+    cancel to ~1e-8 of the terms they are summed from.  The pure element-wise maximum is reported beside it."""
+    import torch
+    import torch.distributed as dist
+
+    n = len(pos_h)
+    frc = md.gather_owned(md.frc).double()
+    counts = torch.zeros(n, dtype=torch.int32, device=dev)
+    own = torch.zeros(n, dtype=torch.int32, device=dev)
+    _lib.check(lib.pantea_neighbor_counts(md.ws.handle, _lib.ptr(own), _lib.stream_ptr()))
+    counts[md.lo:md.hi] = own[md.lo:md.hi]
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    out = None
+    if rank == 0:
+        from oracle import c_oracle  # the checker
+        from oracle.spec import load_potential
+
+        threads = pin_oracle_threads(c_oracle)
+        specs = load_potential(GOLDEN / "h2o.json")
+        t0 = time.perf_counter()
+        _, _, f_o = c_oracle.energy_forces(specs, pos_h, types_h, box_h)
+        row_ptr, _ = c_oracle.neighbors(pos_h, types_h, box_h, 12.0)
+        cpu_s = time.perf_counter() - t0
+        f_o = torch.as_tensor(f_o, device=dev)
+        rtol = 1e-10 if dtype == torch.float64 else 1e-5
+        rms = float(f_o.pow(2).mean().sqrt())
+        err = (frc - f_o).abs()
+        over = float((err / (rtol * (f_o.abs() + rms))).max())
+        rel = float((err / f_o.abs().clamp_min(1e-300)).max())
+        n_equal = bool((counts.cpu().numpy() == np.diff(row_ptr).astype(np.int32)).all())
+        out = {"n_atoms": n, "max_err_over_tol": over, "rtol": rtol, "criterion": "|dF| <= rtol*(|F|+rms(F)) per component",
+               "max_rel_F": rel, "max_abs_dF": float(err.max()), "rms_F": rms, "neighbors_equal": n_equal,
+               "oracle": f"all {n} atoms, oracle/hdnnp_oracle.c, {threads} threads, {cpu_s:.1f} s",
+               "ok": bool(over <= 1.0 and n_equal)}
+    flag = torch.tensor([0.0 if (out is None or out["ok"]) else 1.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if float(flag.item()) != 0.0:
+        if rank == 0:
+            print(json.dumps({"parity": out}), file=sys.stderr)
+        raise SystemExit("bench.py: GPU forces / neighbour counts differ from the oracle; no throughput number is reported")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
@@ -140,7 +204,7 @@ def run_reference(args) -> None:
     specs = load_potential(GOLDEN / "h2o.json")
     pos, types, box = water_box(args.atoms)
     n = len(pos)
-    threads = c_oracle.num_threads()
+    threads = pin_oracle_threads(c_oracle)
     # size the per-step sample for ~3 s of CPU work
     t0 = time.perf_counter()
     c_oracle.energy_forces(specs, pos, types, box, begin=0, end=min(n, 512))
@@ -161,7 +225,8 @@ def run_reference(args) -> None:
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(n), "note": "reference JAX path not runnable here; oracle port timed",
                    "reference_install": ref_status},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "host_cpus": host_cpus(), "kind": "port",
+                         "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -270,9 +335,10 @@ def run_b200(args) -> None:
         all_reduce_max(ms_t)
         return float(ms_t.item()), wall_s, n_launch
 
-    settle_capacities()
+    parity = None if args.no_parity else parity_check(md, lib, _lib, pos_h, types_h, box_h, dtype, rank, world, dev)
+    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None  # before the warm-up: the timed region
+    settle_capacities()                                                        # alone is shorter than a sampling period
     barrier()
-    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
     ms_total, wall, launches = timed_steps(args.steps)
     clocks = sampler.stop() if sampler else None
     value = n * args.steps / (ms_total * 1e-3)
@@ -442,6 +508,7 @@ def run_b200(args) -> None:
         from oracle.spec import load_potential
 
         specs = load_potential(GOLDEN / "h2o.json")
+        pin_oracle_threads(c_oracle)
         t0 = time.perf_counter()
         c_oracle.energy_forces(specs, pos_h, types_h, box_h, begin=0, end=min(n, 512))
         rate = min(n, 512) / (time.perf_counter() - t0)
@@ -449,7 +516,7 @@ def run_b200(args) -> None:
         t0 = time.perf_counter()
         c_oracle.energy_forces(specs, pos_h, types_h, box_h, begin=0, end=m)
         el = time.perf_counter() - t0
-        cpu = {"value": m / el, "unit": UNIT, "cores": c_oracle.num_threads(), "kind": "port",
+        cpu = {"value": m / el, "unit": UNIT, "cores": c_oracle.num_threads(), "host_cpus": host_cpus(), "kind": "port",
                "sample": f"one force+energy evaluation of {m} of the {n} atoms ({el:.1f} s); oracle/hdnnp_oracle.c, "
                          "OpenMP, cell-list gather; the reference's JAX path cannot run here (no jax)"}
 
@@ -462,6 +529,7 @@ def run_b200(args) -> None:
                        "l2": "flushed between timed steps (256 MB write)" if not args.no_flush else "not flushed",
                        "max_neighbors_seen": int(mx.value), "force_mode": "reference (central-role gradient)",
                        "trajectory": f"timed steps replay {SEGMENT}-step segments from the initial state (untimed reset)"},
+            "parity": parity,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "verlet_skin": skin_info, "halo_exchange": halo_info,
             "wall_s_timed_region": wall,

@@ -168,6 +168,20 @@ int pantea_acsf_compute(pantea_workspace* ws, int32_t element, const int32_t* ce
 int pantea_energy_forces(pantea_workspace* ws, void* e_atom, void* forces, void* e_total, int32_t force_mode,
                          void* stream);
 
+/* Evaluations that qualify -- PANTEA_F64, gradients requested, cell-list rows of a box that needs no minimum image on
+   r_jk (every box length >= 4 r_cutoff), at least 64 atoms per SM, a potential with one tanhu cutoff per element whose
+   angular groups are single G3 members with integer zeta -- run on specialised kernels (csrc/acsf2.cu: per-neighbour
+   radial weights, r_jk from the unit-vector dot product).  Same results within ~1e-13 relative.  enable = 0 keeps every
+   call on the generic kernels (diagnostics / parity tests); returns the previous setting.  Process-wide. */
+int pantea_set_fast_path(int32_t enable);
+/* Gaussian screening of the specialised kernels: within one angular group of one centre, a triplet whose Gaussian weight
+   exp(-eta (r_ij^2 + r_ik^2 + r_jk^2)) is below exp(-threshold) times the weight of the pair formed by the centre's two
+   nearest neighbours of the group's types is not evaluated (it is dropped when the pair lists are built).  Active only
+   when those two neighbours lie within r_cutoff of each other (the reference pair is then a live triplet) and no Verlet
+   skin is set.  With the default threshold 40 (4e-18) the dropped terms of a centre sum to < 1e-14 of the symmetry
+   function; 0 disables.  Returns the previous threshold.  Process-wide. */
+double pantea_set_gauss_screen(double threshold);
+
 /* -- molecular dynamics pieces: replace `_get_verlet_new_positions/_velocities`, `_wrap_into_box`,
       `_get_kinetic_energy`, `_get_rescaled_velocities` (reference molecular_dynamics.py:16-30, box.py:123-126,
       system.py:20-29, thermostat.py:12-22).  No mass enters the integrator (as the reference).

@@ -7,13 +7,15 @@ library is missing, or no CUDA device is visible, the compute entry points raise
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional
 
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libpantea_b200.so"
+# PANTEA_B200_LIB selects another build of the same library (kernel-variant experiments, tools/build_variant.py)
+LIB_PATH = Path(os.environ["PANTEA_B200_LIB"]) if os.environ.get("PANTEA_B200_LIB") else _PKG / "libpantea_b200.so"
 
 PANTEA_OK, PANTEA_EINVAL, PANTEA_ECUDA, PANTEA_ECAPACITY, PANTEA_ENOMEM = 0, -1, -2, -3, -4
 PANTEA_F64, PANTEA_F32 = 64, 32
@@ -80,6 +82,8 @@ PROTOTYPES = {
     "pantea_bench_fma": (C.c_int, [_I32, _I32, _I32, _I32, _VP, C.POINTER(_DBL), _VP]),
     "pantea_l2_flush": (C.c_int, [_VP, _I64, _VP]),
     "pantea_workspace_set_counters": (C.c_int, [_VP, _VP]),
+    "pantea_set_fast_path": (C.c_int, [_I32]),
+    "pantea_set_gauss_screen": (_DBL, [_DBL]),
     "pantea_workspace_set_skin": (C.c_int, [_VP, _DBL]),
     "pantea_neighbor_rebuilds": (C.c_int, [_VP, C.POINTER(_I64), _VP]),
     "pantea_scaler_stats": (C.c_int, [_VP, _I64, _I64, _I64, _I32, _VP, _VP]),

@@ -18,168 +18,12 @@
 //     backward (lanes over neurons) -> E_i and F_i = -sum_s dE_i/dG_s dG_s/dr_i (central-role gradient: no scatter).
 //
 // All arithmetic is on the CUDA cores: the path is FP64/FP32-pipe bound, not a GEMM.
-#include "internal.cuh"
-#include "math.cuh"
+#include <atomic>
+#include <cstdlib>
 
-#ifndef PANTEA_EVAL_MINBLOCKS
-#define PANTEA_EVAL_MINBLOCKS 4  // resident 128-thread blocks per SM the FP64 evaluation kernel is compiled for
-#endif
-#ifndef PANTEA_TRIPLETS_PER_LANE
-#define PANTEA_TRIPLETS_PER_LANE 1
-#endif
+#include "acsf_common.cuh"
 
 namespace pantea {
-
-constexpr unsigned kFullMask = 0xffffffffu;
-constexpr int kEvalWarps = 4;       // eval kernel: 4 warps per block, shared by 4 / WPA atoms (WPA = warps per atom)
-#ifndef PANTEA_EVAL_WPA
-#define PANTEA_EVAL_WPA 1           // warps per atom when there are enough atoms to fill the GPU
-#endif
-constexpr int kFilterWarps = 8;     // pair filter: 8 warps per block, one atom each
-constexpr int kNU = PANTEA_TRIPLETS_PER_LANE;
-#ifndef PANTEA_STAGE_ITERS
-#define PANTEA_STAGE_ITERS 8
-#endif
-constexpr int kStageIters = PANTEA_STAGE_ITERS;  // pair-list iterations staged per cp.async group
-
-struct BoxArgK {
-    double lx, ly, lz;
-    int has_box;
-};
-
-template <typename T>
-struct AtomArgs {
-    const Rec<T>* rec;
-    const int32_t* nbr;
-    const int32_t* tcount;
-    int cap;   // row stride of `nbr`
-    int scap;  // neighbour records staged in shared memory (<= cap; longer rows raise the overflow flag)
-    int32_t* flags;
-    const int32_t* slot_of;
-    const int32_t* struct_of;
-    const double* boxes;
-    BoxArgK box;
-    int wrap_jk;
-    double rc_list;  // radius the neighbour rows were built with (cutoff + Verlet skin)
-    float skin;      // Verlet skin: the pair lists must stay valid while atoms move by up to skin / 2 each
-    const int32_t* filter_guard;  // skin: the filter is skipped while *filter_guard == 0 (NULL: always run)
-    const ElementTable* tables;
-    int n_types;
-    int element_slot;  // >= 0: apply this element's table to every centre; -1: the atom's own type
-    const int32_t* centres;
-    int n_work;
-    int by_slot;  // 1: work item = cell-sorted slot (energy/force pass); 0: work item = centre list entry
-    int own_begin, own_end;
-    const int32_t* owned_slots;  // by_slot passes of a block-owned rank: work item -> slot (NULL: work item = slot)
-    // pair lists written by the filter, read by the evaluation
-    int32_t* pairs;      // [n_work][pair_cap]  (j | k << 16), row positions within the staged neighbour block
-    int32_t* pair_off;   // [n_work][max_groups + 1] offsets of each group's segment
-    int pair_cap, max_groups;
-    T* G;
-    T* dG;
-    int g_stride;
-    T* e_atom;
-    T* forces;
-    T* gbuf;  // [n_work][n_sf_max][4] summed descriptors handed from the evaluation to the network kernel
-    T* wbuf;  // full-force mode: [n_work][n_sf_max] dE_i/dG_is written by the network kernel, read by the scatter pass
-    unsigned long long* counters;  // optional work counters: [0] pairs, [1] radial-SF evals, [2] triplet-SF evals
-    int n_cls_max, n_sf_max, n_neurons_max, width_max;
-};
-
-template <typename T>
-__host__ __device__ inline size_t eval_smem_bytes(int cap, int n_cls, int n_sf, int n_neurons, int width, int wpa) {
-    size_t t_elems = (size_t)(5 + 2 * n_cls) * (cap + 1)  // neighbour records + one all-zero padding record
-                     + (size_t)wpa * n_sf * 4;            // per-warp partial sums
-    (void)n_neurons; (void)width;
-    return (t_elems * sizeof(T) + 15) & ~size_t(15);
-}
-
-template <typename T>
-__device__ __forceinline__ T powi(T base, int n) {
-    T r = (T)1;
-    while (n > 0) {
-        if (n & 1) r *= base;
-        base *= base;
-        n >>= 1;
-    }
-    return r;
-}
-
-// rarely used, large library routines are kept out of line so that the hot loops stay small
-template <typename T>
-__device__ __noinline__ T pow_general(T base, T e) { return t_pow<T>(base, e); }
-template <typename T>
-__device__ __noinline__ void cutoff_eval_ool(int type, T r, T rc, T* fc, T* dfc) {
-    T a, b;
-    cutoff_eval<T>(type, r, rc, a, b);
-    *fc = a; *dfc = b;
-}
-template <typename T>
-__device__ __noinline__ void activation_eval_ool(int act, T x, T* y, T* dy) {
-    T a, b;
-    activation_eval<T>(act, x, a, b);
-    *y = a; *dy = b;
-}
-
-// barrier over the WPA warps of one atom (several atoms share a block: named barriers 1.., one per atom)
-template <int WPA>
-__device__ __forceinline__ void group_sync(int atom_in_block) {
-    if (WPA == 1) __syncwarp();
-    else if (WPA == kEvalWarps) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" ::"r"(atom_in_block + 1), "n"(WPA * 32) : "memory");
-}
-
-// work item -> (cell-ordered slot, output row, element table); false when the item is not evaluated
-template <typename T>
-__device__ __forceinline__ bool resolve_item(const AtomArgs<T>& a, int w, int& slot, int& out_row, int& etype) {
-    if (a.by_slot) {
-        slot = a.owned_slots ? a.owned_slots[w] : w;
-        out_row = rec_idx(a.rec[slot]);
-        if (out_row < a.own_begin || out_row >= a.own_end) return false;
-    } else {
-        const int oi = a.centres ? a.centres[w] : w;
-        slot = a.slot_of[oi];
-        out_row = w;
-    }
-    etype = a.element_slot >= 0 ? a.element_slot : rec_type(a.rec[slot]);
-    return true;
-}
-
-template <typename T>
-__device__ __forceinline__ void item_box(const AtomArgs<T>& a, int slot, T& lx, T& ly, T& lz, bool& pbc) {
-    lx = (T)a.box.lx; ly = (T)a.box.ly; lz = (T)a.box.lz;
-    pbc = a.box.has_box != 0;
-    if (a.boxes) {
-        const int s = a.struct_of[slot];
-        lx = (T)a.boxes[3 * s]; ly = (T)a.boxes[3 * s + 1]; lz = (T)a.boxes[3 * s + 2];
-        pbc = true;
-    }
-}
-
-// neighbour segments by type bucket: seg[b] .. seg[b+1] within the (type-partitioned) row, clamped to `total`
-struct Segments {
-    int seg[kBuckets + 1];
-    int total;
-    __device__ __forceinline__ void load(const int32_t* tc, int cap) {
-        int acc = 0;
-#pragma unroll
-        for (int b = 0; b < kBuckets; ++b) { seg[b] = acc; acc += tc[b]; }
-        seg[kBuckets] = acc;
-        total = acc < cap ? acc : cap;
-    }
-    __device__ __forceinline__ int lo(int t) const {
-        int v = 0;
-#pragma unroll
-        for (int b = 0; b < kBuckets; ++b) if (b == t) v = seg[b];
-        return v < total ? v : total;
-    }
-    __device__ __forceinline__ int hi(int t) const {
-        int v = 0;
-#pragma unroll
-        for (int b = 0; b < kBuckets; ++b) if (b == t) v = seg[b + 1];
-        return v < total ? v : total;
-    }
-};
 
 // ------------------------------------------------------------------------------------------------
 // 1. pair pre-filter
@@ -458,10 +302,11 @@ __device__ __forceinline__ void angular_group(const ElementTable& tab, const Ang
                         if (!LEAN && m_iz[m] != 1)  // warp-uniform; FAST groups only hold integer zeta >= 1
                             pw1 = (FAST || m_iz[m] > 1) ? powi<T>(bs, m_iz[m] - 1) : pow_general<T>(bs, m_zm1[m]);
                         const T ep = e[u] * fprod[u] * pw1;
-                        const T ap = m_pref[m] * bs * ep;  // this triplet's contribution to G
+                        // zeta == 0: x^0 = 1 also at x = 0 (the reference's pow), where bs * bs^-1 would be NaN
+                        const T ap = (!FAST && m_iz[m] == 0) ? m_pref[m] * e[u] * fprod[u] : m_pref[m] * bs * ep;
                         aG[m] += ap;
                         if (GRAD) {
-                            const T Tc = m_zl[m] * ep;
+                            const T Tc = (!FAST && m_iz[m] == 0) ? (T)0 : m_zl[m] * ep;
                             const T Bj = Tc * (ivk[u] - cost[u] * ivj[u]) + ap * (qj[u] + m_2neta[m] * rj[u]);
                             const T Bk = Tc * (ivj[u] - cost[u] * ivk[u]) + ap * (qk[u] + m_2neta[m] * rk[u]);
                             aX[m] = fma(Bk, uxk[u], fma(Bj, uxj[u], aX[m]));
@@ -530,6 +375,8 @@ hdnnp_eval_kernel(const AtomArgs<T> a) {
     Segments sg;
     sg.load(a.tcount + (size_t)slot * kBuckets, cap);
     const int total = sg.total;
+    // a row longer than the staged capacity is cut here: report it (radial-only potentials launch no pair filter)
+    if (sg.seg[kBuckets] > cap && lane == 0 && wrank == 0) atomicMax(&a.flags[1], sg.seg[kBuckets]);
 
     // ---- stage the neighbour block (two neighbours per thread in flight: gather latency) ------------
     {
@@ -787,6 +634,7 @@ __global__ void __launch_bounds__(kFullWarps * 32) full_force_kernel(const AtomA
     Segments sg;
     sg.load(a.tcount + (size_t)slot * kBuckets, cap);
     const int total = sg.total;
+    if (sg.seg[kBuckets] > cap && lane == 0) atomicMax(&a.flags[1], sg.seg[kBuckets]);
     {
         const int32_t* row = a.nbr + (size_t)slot * a.cap;
         const int n_cls = tab.n_cls;
@@ -868,8 +716,9 @@ __global__ void __launch_bounds__(kFullWarps * 32) full_force_kernel(const AtomA
                     const T bs = (T)1 + lam * cost;
                     T pw1 = (T)1;
                     if (mem.izeta != 1) pw1 = mem.izeta > 1 ? powi<T>(bs, mem.izeta - 1) : pow_general<T>(bs, (T)(mem.zeta - 1.0));
-                    const T ee = t_exp<T>(-eta * r2) * pw1 * (T)mem.pref;   // pref (1 + lambda c)^(zeta-1) exp(-eta r2)
-                    const T A = ee * bs;                                     // pref (1 + lambda c)^zeta exp(-eta r2)
+                    const bool z0 = mem.izeta == 0;  // x^0 = 1 also at x = 0 (the reference's pow)
+                    const T ee = z0 ? (T)0 : t_exp<T>(-eta * r2) * pw1 * (T)mem.pref;  // pref (1 + lambda c)^(zeta-1) exp(-eta r2)
+                    const T A = z0 ? t_exp<T>(-eta * r2) * (T)mem.pref : ee * bs;      // pref (1 + lambda c)^zeta exp(-eta r2)
                     const T Tc = wm * (T)(mem.zeta * mem.lambda0) * ee * (fcj * fck * fcjk);
                     const T Tj = wm * A * fck * fcjk * (dfj - (T)2 * eta * rj * fcj);
                     const T Tk = wm * A * fcj * fcjk * (dfk - (T)2 * eta * rk * fck);
@@ -959,19 +808,33 @@ int reduce_energy(pantea_workspace* ws, const void* e_atom, void* e_total, cudaS
 // ------------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: `configured` is indexed by the current device
+int opt_in_smem(const void* kern, size_t smem, size_t* configured, const char* what) {
+    int dev = 0;
+    PANTEA_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(PANTEA_EINVAL, "device index out of range");
+    if (smem > configured[dev]) {
+        if (smem > 227 * 1024) return fail(PANTEA_EINVAL, what);
+        PANTEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = smem;
+    }
+    return PANTEA_OK;
+}
+static int g_num_sms_dev[64] = {0};  // per device
+// pantea_set_fast_path: 1 (default; PANTEA_EVAL_V2=0 in the environment starts with 0) lets qualifying evaluations take
+// the specialised kernels of acsf2.cu, 0 keeps everything on the generic kernels of this file
+// pantea_set_gauss_screen: threshold T of the fast path's Gaussian screening (0: off)
+static std::atomic<double> g_gauss_screen{[]() { const char* e = std::getenv("PANTEA_GAUSS_SCREEN"); return e ? std::atof(e) : 40.0; }()};
+static std::atomic<int> g_fast_path{[]() { const char* e = std::getenv("PANTEA_EVAL_V2"); return (e && e[0] == '0') ? 0 : 1; }()};
 
 template <typename T, int WPA, bool GRAD, int MCH>
 static int launch_eval(const AtomArgs<T>& args, cudaStream_t st) {
     const int apb = kEvalWarps / WPA;
     const size_t smem = apb * eval_smem_bytes<T>(args.scap, args.n_cls_max, args.n_sf_max, args.n_neurons_max, args.width_max, WPA);
     auto kern = hdnnp_eval_kernel<T, WPA, GRAD, MCH>;
-    static size_t configured = 0;  // per instantiation
-    if (smem > configured) {
-        if (smem > 227 * 1024) return fail(PANTEA_EINVAL, "neighbour capacity / potential too large for shared memory");
-        PANTEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static size_t configured[64] = {0};  // per instantiation and device
+    int rc_s = opt_in_smem((const void*)kern, smem, configured, "neighbour capacity / potential too large for shared memory");
+    if (rc_s != PANTEA_OK) return rc_s;
     const int blocks = (args.n_work + apb - 1) / apb;
     kern<<<blocks, apb * WPA * 32, smem, st>>>(args);
     PANTEA_LAUNCH_CHECK();
@@ -990,17 +853,17 @@ template <typename T>
 static int launch_filter(const AtomArgs<T>& a, cudaStream_t st) {
     const size_t smem = (size_t)kFilterWarps * (a.scap + 1) * sizeof(float4);
     auto kern = pair_filter_kernel<T>;
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (smem > 227 * 1024) return fail(PANTEA_EINVAL, "neighbour capacity too large for shared memory");
-        PANTEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static size_t configured[64] = {0};
+    int rc_s = opt_in_smem((const void*)kern, smem, configured, "neighbour capacity too large for shared memory");
+    if (rc_s != PANTEA_OK) return rc_s;
     const int blocks = (a.n_work + kFilterWarps - 1) / kFilterWarps;
     kern<<<blocks, kFilterWarps * 32, smem, st>>>(a);
     PANTEA_LAUNCH_CHECK();
     return PANTEA_OK;
 }
+
+static int launch_v2_dispatch(const AtomArgs<double>& a, cudaStream_t st) { return launch_v2(a, st); }
+static int launch_v2_dispatch(const AtomArgs<float>&, cudaStream_t) { return fail(PANTEA_EINVAL, "fast path is double precision only"); }
 
 // pair-list storage: [max_atoms][pair_cap] entries + [max_atoms][max_groups + 1] offsets
 static int ensure_pair_storage(pantea_workspace* ws) {
@@ -1012,7 +875,7 @@ static int ensure_pair_storage(pantea_workspace* ws) {
     if (ws->pairs) cudaFree(ws->pairs);
     if (ws->pair_off) cudaFree(ws->pair_off);
     ws->pairs = ws->pair_off = nullptr;
-    cudaError_t err = cudaMalloc((void**)&ws->pairs, sizeof(int32_t) * (size_t)ws->max_atoms * want);
+    cudaError_t err = cudaMalloc((void**)&ws->pairs, sizeof(int32_t) * ((size_t)ws->max_atoms * want + 1024));
     if (err == cudaSuccess) err = cudaMalloc((void**)&ws->pair_off, sizeof(int32_t) * (size_t)ws->max_atoms * (pot->max_groups + 1));
     if (err != cudaSuccess)
         return fail(err == cudaErrorMemoryAllocation ? PANTEA_ENOMEM : PANTEA_ECUDA,
@@ -1043,6 +906,7 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
     a.wrap_jk = ws->boxes ? 1 : (ws->has_box && 0.5 * lmin < 2.0 * ws->rc * (1.0 + 1e-9) ? 1 : 0);
     a.rc_list = ws->rc;
     a.skin = ws->skin_active ? (float)ws->skin : 0.f;
+    a.screen_t = a.skin > 0.f ? 0.f : (float)g_gauss_screen.load(std::memory_order_relaxed);  // (kept lists must not depend on the positions)
     a.filter_guard = nullptr;
     a.tables = pot->dev; a.n_types = pot->n_elements; a.element_slot = element_slot;
     a.centres = centres;
@@ -1079,19 +943,32 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
     a.n_neurons_max = pot->max_neurons; a.width_max = pot->max_width;
     if (a.n_work == 0) return PANTEA_OK;
     if (a.n_work > ws->max_atoms) return fail(PANTEA_EINVAL, "more centres than the workspace capacity");
-    if (g_num_sms == 0) {
-        int dev = 0;
-        PANTEA_CUDA_TRY(cudaGetDevice(&dev));
-        PANTEA_CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    if (pot->max_groups > 0) {
+    int dev_now = 0;
+    PANTEA_CUDA_TRY(cudaGetDevice(&dev_now));
+    if (dev_now < 0 || dev_now >= 64) return fail(PANTEA_EINVAL, "device index out of range");
+    if (g_num_sms_dev[dev_now] == 0)
+        PANTEA_CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms_dev[dev_now], cudaDevAttrMultiProcessorCount, dev_now));
+    const int g_num_sms = g_num_sms_dev[dev_now];
+    const bool grad = dG != nullptr || forces != nullptr;
+    // few atoms: several warps per atom so that every SM sub-partition has work.  The energy pass decides on the
+    // system size, not on this rank's share: the summation order -- hence every bit of the result -- is then the same
+    // on 1 and on N GPUs
+    const bool wide = (int64_t)(energy_pass ? (int)ws->n : a.n_work) < (int64_t)g_num_sms * 64;
+    // fast path (acsf2.cu): double precision with gradients, cell-list rows of a box that needs no minimum image on
+    // r_jk, a potential whose tables qualify, no work counters; its pair lists have their own format
+    const bool use_v2 = g_fast_path.load(std::memory_order_relaxed) != 0 && sizeof(T) == 8 && pot->v2_ok && grad && !wide && !a.wrap_jk &&
+                        ws->mode == kModeCell && (a.scap + 1) * 80 < 65536;
+    if (ws->lists_v2 != use_v2) ws->lists_valid = false;  // (Verlet skin) lists kept from a pass in the other format
+    ws->lists_v2 = use_v2;
+    if (pot->max_groups > 0 || use_v2) {
         // Verlet skin: the energy pass keeps its pair lists until the neighbour rows are rebuilt (device flag)
         const bool reuse = energy_pass && ws->skin_active;
         if (reuse) {
             if (!ws->lists_valid) PANTEA_CUDA_TRY(cudaMemsetAsync(ws->skin_flags + 1, 1, 4, st));
             a.filter_guard = ws->skin_flags + 1;
         }
-        rc = launch_filter<T>(a, st);
+        if (use_v2) rc = launch_v2_dispatch(a, st);
+        else rc = launch_filter<T>(a, st);
         if (rc != PANTEA_OK) return rc;
         if (reuse) {
             skin_lists_fresh_kernel<<<1, 1, 0, st>>>(ws->skin_flags);
@@ -1099,25 +976,18 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
         }
         ws->lists_valid = reuse;
     }
-    const bool grad = dG != nullptr || forces != nullptr;
     const int mm = pot->max_members;
-    // few atoms: several warps per atom so that every SM sub-partition has work.  The energy pass decides on the
-    // system size, not on this rank's share: the summation order -- hence every bit of the result -- is then the same
-    // on 1 and on N GPUs
-    const bool wide = (int64_t)(energy_pass ? (int)ws->n : a.n_work) < (int64_t)g_num_sms * 64;
-    if (wide) rc = grad ? launch_mch<T, 4, true>(a, mm, st) : launch_mch<T, 4, false>(a, mm, st);
+    if (use_v2) rc = PANTEA_OK;  // filter and evaluation were launched together above
+    else if (wide) rc = grad ? launch_mch<T, 4, true>(a, mm, st) : launch_mch<T, 4, false>(a, mm, st);
     else rc = grad ? launch_mch<T, PANTEA_EVAL_WPA, true>(a, mm, st) : launch_mch<T, PANTEA_EVAL_WPA, false>(a, mm, st);
     if (rc != PANTEA_OK || !a.gbuf) return rc;
     {
         const int gw = a.width_max > a.n_sf_max ? a.width_max : a.n_sf_max;
         const size_t smem = (size_t)(a.n_sf_max + 2 * a.n_neurons_max + 2 * gw) * kMlpThreads * sizeof(T);
         auto kern = mlp_force_kernel<T>;
-        static size_t configured = 0;
-        if (smem > configured) {
-            if (smem > 227 * 1024) return fail(PANTEA_EINVAL, "network too wide for the per-thread shared-memory scratch");
-            PANTEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        static size_t configured[64] = {0};
+        int rc_s = opt_in_smem((const void*)kern, smem, configured, "network too wide for the per-thread shared-memory scratch");
+        if (rc_s != PANTEA_OK) return rc_s;
         kern<<<(a.n_work + kMlpThreads - 1) / kMlpThreads, kMlpThreads, smem, st>>>(a);
         PANTEA_LAUNCH_CHECK();
     }
@@ -1126,12 +996,9 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
         a.forces = (T*)forces_out;
         const size_t smem = (size_t)kFullWarps * full_smem_bytes<T>(a.scap, a.n_cls_max, a.n_sf_max);
         auto kern = full_force_kernel<T>;
-        static size_t configured = 0;
-        if (smem > configured) {
-            if (smem > 227 * 1024) return fail(PANTEA_EINVAL, "neighbour capacity too large for the full-force pass");
-            PANTEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        static size_t configured[64] = {0};
+        int rc_s = opt_in_smem((const void*)kern, smem, configured, "neighbour capacity too large for the full-force pass");
+        if (rc_s != PANTEA_OK) return rc_s;
         kern<<<(a.n_work + kFullWarps - 1) / kFullWarps, kFullWarps * 32, smem, st>>>(a);
         PANTEA_LAUNCH_CHECK();
     }
@@ -1150,6 +1017,15 @@ int atom_kernel_launch(pantea_workspace* ws, int element_slot, const int32_t* ce
 using namespace pantea;
 
 extern "C" {
+
+int pantea_set_fast_path(int32_t enable) {
+    const int old = g_fast_path.exchange(enable ? 1 : 0);
+    return old;
+}
+
+double pantea_set_gauss_screen(double threshold) {
+    return g_gauss_screen.exchange(threshold > 0.0 ? threshold : 0.0);
+}
 
 int pantea_acsf_compute(pantea_workspace* ws, int32_t element, const int32_t* centres, int64_t n_centres, void* G,
                         void* dG, void* stream) {

@@ -1,0 +1,639 @@
+// Fast path of the symmetry-function evaluation for sm_100a (double precision, values + central gradients).
+//
+// Same mathematics as acsf.cu (reference pantea/descriptors/acsf/acsf.py:163-330, angular.py:51-66, cutoff.py:74-79),
+// specialised for the RuNNer-style potentials the benchmark uses -- one tanhu cutoff class per element, every angular
+// group a single G3 member with integer zeta, every neighbour type in at most one group of its centre, no minimum image
+// on r_jk (box >= 4 rc) -- and rebuilt around the instruction count of the triplet loop, which is what bounds the
+// kernel (FP64 issue):
+//
+//  * per-neighbour weights.  exp(-eta (r_j^2 + r_k^2 + r_jk^2)) fc_j fc_k fc_jk = W_j W_k fc_jk exp(-eta r_jk^2) with
+//    W_n = sqrt(pref) fc(r_n) exp(-eta r_n^2) staged once per neighbour, and the radial part of the gradient collapses
+//    into Q_n = fc'(r_n)/fc(r_n) - 2 eta r_n;
+//  * r_jk^2 = r_j^2 + r_k^2 - 2 r_j r_k cos(theta) from the unit-vector dot product the angular factor needs anyway
+//    (records hold sqrt(2) r so that the product needs no extra factor);
+//  * one cubic-convergence step after the MUFU seeds of the reciprocal root and the reciprocal;
+//  * a 256-entry 2^(i/256) table so that the two exponentials need a degree-4 polynomial;
+//  * 80-byte neighbour records [u_x u_y | u_z r^2 | 1/r sqrt2 r | W Q | fc q] read with four LDS.128 per role
+//    (20-bank stride: conflict-free for consecutive records), pair-list entries that hold the two record byte offsets;
+//  * pair lists padded per group to a multiple of 32 entries with an entry that points at the all-zero record behind
+//    the last neighbour, staged 16 bytes per lane with cp.async: the loop has no bounds, validity or tail handling.
+//
+// The pair filter of this path keeps one partner per lane and accumulates a 32-bit survivor mask over a tile of 32
+// swept neighbours (9 instructions per 32 pair tests), then emits the tile's entries with one warp scan.
+#include "acsf_common.cuh"
+
+namespace pantea {
+
+constexpr int kRec2 = 10;                 // doubles per staged neighbour record
+constexpr int kRec2Bytes = kRec2 * 8;     // 80
+constexpr int kTab2 = 256;                // entries of the 2^(i/256) table
+#ifndef PANTEA_CHUNK2
+#define PANTEA_CHUNK2 8
+#endif
+constexpr int kChunk2 = PANTEA_CHUNK2;    // pair-list iterations per cp.async group (4 or 8)
+constexpr int kFilter2Warps = 8;
+#ifndef PANTEA_NU2
+#define PANTEA_NU2 2
+#endif
+constexpr int kPadTo2f = 32 * PANTEA_NU2;  // list segments are padded to whole loop iterations of the evaluation
+
+__host__ __device__ inline size_t eval2_smem_bytes(int scap, int n_sf) {
+    return ((size_t)(scap + 1) * kRec2Bytes + (size_t)n_sf * 4 * 8 + 15) & ~size_t(15);
+}
+
+// ---- scalar helpers -------------------------------------------------------------------------------------------------
+// Constants of the triplet loop live in constant memory so that they fold into the DFMA operands (c[bank][offset]);
+// written as literals ptxas re-materialises them with two MOVs per use once the register budget is reached.
+static __constant__ double kK2[8] = {
+    0x1.71547652b82fep+8,    // [0] 256 / ln 2
+    6755399441055744.0,      // [1] 1.5 * 2^52
+    -0x1.62e42fee00000p-9,   // [2] -ln2/256 with the low 21 mantissa bits zero: n * kK2[2] is exact
+    -0x1.a39ef35793c76p-41,  // [3] -(ln2/256 - hi)
+    4.16666666666666666667e-02, 1.66666666666666666667e-01,  // [4], [5] 1/24, 1/6
+    0.0, 0.0};
+
+// sqrt(a) for a > 0: MUFU reciprocal-root seed (>= 20 good bits) and one step of cubic convergence,
+// a y (1 + h/2 + 3 h^2/8) with h = 1 - a y^2, arranged so that every constant is an FP64 immediate
+__device__ __forceinline__ double sqrt_cubic(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double ay = a * y;
+    const double h = fma(-ay, y, 1.0);
+    const double u = h * 0.5, v = h * 0.75;
+    return fma(ay, fma(u, v, u), ay);
+}
+// 1/a: MUFU seed, one cubic step r += r (e + e^2), e = 1 - a r
+__device__ __forceinline__ double rcp_cubic(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    const double e = fma(-a, r, 1.0);
+    return fma(r, fma(e, e, e), r);
+}
+
+// exp(y) = 2^k T[i] p(f), n = round(y 256/ln2) = 256 k + i, f = y - n ln2/256, |f| <= ln2/512, p of degree 4
+// (truncation f^5/120 < 4e-17).  |y| < 700 guaranteed by the caller.
+__device__ __forceinline__ double exp_tab256(double y, const double* __restrict__ tab) {
+    const double t = fma(y, kK2[0], kK2[1]);
+    const int n = __double2loint(t);
+    const double nf = t - kK2[1];
+    double f = fma(nf, kK2[2], y);
+    f = fma(nf, kK2[3], f);
+    double p = fma(f, kK2[4], kK2[5]);
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    p *= tab[n & (kTab2 - 1)];
+    return __hiloint2double(__double2hiint(p) + (n >> 8) * 0x100000, __double2loint(p));
+}
+// max(x, ~0) for finite x through the sign / exponent word: negative values (and -0) come out as a positive number
+// below 1e-308 + (hi >= `floor_hi`); one integer instruction instead of the NaN-aware FP64 maximum
+__device__ __forceinline__ double clamp_hi(double x, int floor_hi) {
+    return __hiloint2double(max(__double2hiint(x), floor_hi), __double2loint(x));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+struct __align__(16) D2 { double a, b; };
+__device__ __forceinline__ D2 lds128(const unsigned char* p) { return *reinterpret_cast<const D2*>(p); }
+
+// ------------------------------------------------------------------------------------------------
+// pair filter
+// ------------------------------------------------------------------------------------------------
+constexpr int kStrip2 = 1024 + 128;  // entries of a warp's emission strip: one full tile behind an unflushed remainder
+
+// State of one warp's walk over the angular groups of its atom.
+struct Filter2 {
+    const float4* sf4;   // staged (dx, dy, dz, r^2) of the neighbours
+    int32_t* list;       // the atom's pair list in global memory
+    int32_t* strip;      // the warp's shared-memory emission strip
+    int pair_cap, off, fill, lane;
+    float rc2f;
+    float r2max;  // Gaussian screening: pairs with r_j^2 + r_k^2 + r_jk^2 above it are dropped (huge: no screening)
+    bool cls_test, screen;
+
+    // compacts `mask` (bit b <-> entry e0 + b * stride; DIAG: minus wrap_sub from bit wrap_b on) into the strip, then
+    // flushes the strip's full 128-entry blocks with one 16-byte store per lane
+    template <bool DIAG>
+    __device__ __forceinline__ void emit(unsigned mask, int nb, int e0, int stride, int wrap_b, int wrap_sub) {
+        const int c = __popc(mask);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(kFullMask, incl, 31);
+        int32_t* q = strip + fill + (incl - c);
+        for (int b0 = 0; b0 < nb; b0 += 8) {
+            const unsigned m8 = mask >> b0;
+            int e = e0 + b0 * stride;
+            if (DIAG && b0 > wrap_b) e -= wrap_sub;
+#pragma unroll
+            for (int b = 0; b < 8; ++b, e += stride) {
+                if (DIAG && b0 + b == wrap_b) e -= wrap_sub;
+                if (m8 & (1u << b)) *q++ = e;
+            }
+        }
+        fill += total;
+        __syncwarp();
+        const int nblk = fill >> 7;
+        if (nblk > 0) {
+            if (off + nblk * 128 <= pair_cap)  // warp-uniform; an overflowing list is only counted
+                for (int blk = 0; blk < nblk; ++blk)
+                    *reinterpret_cast<int4*>(list + off + blk * 128 + 4 * lane) = *reinterpret_cast<const int4*>(strip + blk * 128 + 4 * lane);
+            const int rem = fill & 127;
+            int4 keep = make_int4(0, 0, 0, 0);
+            if (4 * lane < rem) keep = *reinterpret_cast<const int4*>(strip + nblk * 128 + 4 * lane);
+            __syncwarp();
+            if (4 * lane < rem) *reinterpret_cast<int4*>(strip + 4 * lane) = keep;
+            off += nblk * 128;
+            fill = rem;
+            __syncwarp();
+        }
+    }
+
+    // ends a group's segment: pads it to whole loop iterations of the evaluation and writes the strip's remainder out
+    __device__ __forceinline__ int finish_group(int pad_entry) {
+        const int padn = (-(off + fill)) & (kPadTo2f - 1);
+        for (int e = lane; e < padn; e += 32) strip[fill + e] = pad_entry;
+        fill += padn;
+        __syncwarp();
+        if (off + fill <= pair_cap)
+            for (int e = lane; e < fill; e += 32) list[off + e] = strip[e];
+        off += fill;
+        fill = 0;
+        __syncwarp();
+        return padn;
+    }
+
+    // resident chunk (lanes hold staged neighbours r0 + lane, lane < nres; their record offset goes into the entry half
+    // selected by res_shift) against the swept range [s_begin, s_begin + ns): tiles of 32 broadcast reads
+    __device__ __forceinline__ void rect(int r0, int nres, int res_shift, int s_begin, int ns) {
+        const float4 fl = sf4[r0 + (lane < nres ? lane : 0)];
+        const bool l_ok = lane < nres && (!cls_test || fl.w < rc2f);
+        const int res_part = ((r0 + lane) * kRec2Bytes) << res_shift;
+        const int stride = kRec2Bytes << (16 - res_shift);
+        const float al = r2max - fl.w;  // screening: r_jk^2 must stay below al - r_s^2
+        for (int s0 = 0; s0 < ns; s0 += 32) {
+            const int nb = min(32, ns - s0);
+            unsigned mask = 0;
+            const float4* p = sf4 + s_begin + s0;
+            for (int b0 = 0; b0 < nb; b0 += 8, p += 8) {  // blocks of eight steps with compile-time bit positions; a
+                unsigned m8 = 0;                           // partial block reads past the range (inside the staging array)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const float4 fs = p[b];  // warp-uniform address: broadcast
+                    const float ex = fs.x - fl.x, ey = fs.y - fl.y, ez = fs.z - fl.z;
+                    const float d2 = ex * ex + ey * ey + ez * ez;
+                    const float thr = screen ? fminf(rc2f, al - fs.w) : rc2f;
+                    if (d2 < thr) m8 |= 1u << b;
+                }
+                mask |= m8 << b0;
+            }
+            if (nb < 32) mask &= (1u << nb) - 1u;
+            if (cls_test) mask &= __ballot_sync(kFullMask, lane < nb && sf4[s_begin + s0 + lane].w < rc2f);
+            if (!l_ok) mask = 0;
+            emit<false>(mask, nb, res_part + (((s_begin + s0) * kRec2Bytes) << (16 - res_shift)), stride, 0, 0);
+        }
+    }
+
+    // unordered pairs inside [r0, r0 + nres), nres <= 32: lane L meets (L + s) mod nres for s = 1 .. nres / 2 (for even
+    // nres the last step only on the lower half of the lanes), i.e. every pair once with all lanes busy
+    __device__ __forceinline__ void diag(int r0, int nres) {
+        if (nres < 2) return;
+        const bool l_in = lane < nres;
+        const float4 fl = sf4[r0 + (l_in ? lane : 0)];
+        const bool l_ok = l_in && (!cls_test || fl.w < rc2f);
+        const float al = r2max - fl.w;
+        const int h = nres >> 1;
+        unsigned mask = 0;
+        int pidx = lane + 1;  // partner of step s = 1
+        for (int s = 1; s <= h; ++s, ++pidx) {
+            if (pidx >= nres) pidx -= nres;
+            const float4 fs = sf4[r0 + (l_in ? pidx : 0)];
+            const float ex = fs.x - fl.x, ey = fs.y - fl.y, ez = fs.z - fl.z;
+            const float d2 = ex * ex + ey * ey + ez * ez;
+            bool live = d2 < (screen ? fminf(rc2f, al - fs.w) : rc2f) && (!cls_test || fs.w < rc2f);
+            if (s == h && !(nres & 1)) live = live && lane < h;
+            if (live) mask |= 1u << (s - 1);
+        }
+        if (!l_ok) mask = 0;
+        // entry: lane's record in the low half, partner L + 1 + b (minus nres once it wraps) in the high half
+        const int e0 = ((r0 + lane) * kRec2Bytes) | (((r0 + lane + 1) * kRec2Bytes) << 16);
+        emit<true>(mask, h, e0, kRec2Bytes << 16, nres - 1 - lane, (nres * kRec2Bytes) << 16);
+    }
+};
+
+#ifndef PANTEA_FILTER2_MINBLOCKS
+#define PANTEA_FILTER2_MINBLOCKS 3
+#endif
+template <typename T>
+__global__ void __launch_bounds__(kFilter2Warps * 32, PANTEA_FILTER2_MINBLOCKS) pair_filter2_kernel(const AtomArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.filter_guard && *a.filter_guard == 0) return;  // rows unchanged since the lists were written
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * kFilter2Warps + wib;
+    if (w >= a.n_work) return;
+    int slot, out_row, etype;
+    if (!resolve_item(a, w, slot, out_row, etype)) return;
+    int32_t* off_out = a.pair_off + (size_t)w * (a.max_groups + 1);
+    if (etype >= a.n_types) {
+        if (lane == 0) off_out[0] = 0;
+        return;
+    }
+    const ElementTable& tab = a.tables[etype];
+    float4* sf4 = (float4*)smem_raw + (size_t)wib * (a.scap + 32);  // + 32: a partial tile may read past the row
+    int32_t* strip = (int32_t*)((float4*)smem_raw + (size_t)kFilter2Warps * (a.scap + 32)) + wib * kStrip2;
+
+    Segments sg;
+    sg.load(a.tcount + (size_t)slot * kBuckets, a.scap);
+    if (sg.seg[kBuckets] > a.scap && lane == 0) atomicMax(&a.flags[1], sg.seg[kBuckets]);
+
+    T lx, ly, lz;
+    bool pbc;
+    item_box(a, slot, lx, ly, lz, pbc);
+
+    // stage (dx, dy, dz, r^2): differences formed in T, then rounded to float
+    const float rcf = tab.n_cls > 0 ? (float)tab.cls[0].rc + a.skin : 0.f;
+    const float rc2f = rcf * rcf * 1.0001f + 1e-4f;  // inclusive: the exact test is the evaluation's
+    {
+        const Rec<T> ri = a.rec[slot];
+        const int32_t* row = a.nbr + (size_t)slot * a.cap;
+        // all index loads of up to five 32-neighbour rounds in flight, then all record gathers
+        constexpr int RB = 5;
+        for (int base = 0; base < sg.total; base += 32 * RB) {
+            int idx[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int n = base + 32 * r + lane;
+                idx[r] = row[n < sg.total ? n : sg.total - 1];
+            }
+            Rec<T> rr[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) rr[r] = a.rec[idx[r]];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int n = base + 32 * r + lane;
+                if (n < sg.total) {
+                    T dx = sub_rn(ri.x, rr[r].x), dy = sub_rn(ri.y, rr[r].y), dz = sub_rn(ri.z, rr[r].z);
+                    if (pbc) { dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz); }
+                    const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
+                    const float r2 = fx * fx + fy * fy + fz * fz;
+                    sf4[n] = make_float4(fx, fy, fz, r2);
+                }
+            }
+        }
+    }
+    __syncwarp();
+
+    Filter2 f;
+    f.sf4 = sf4; f.list = a.pairs + (size_t)w * a.pair_cap; f.strip = strip; f.pair_cap = a.pair_cap; f.off = 0; f.fill = 0;
+    f.lane = lane; f.rc2f = rc2f;
+    f.cls_test = tab.n_cls > 0 && tab.cls[0].rc + (double)a.skin < a.rc_list;  // rows reach beyond the cutoff
+    const int pad_entry = (sg.total * kRec2Bytes) | ((sg.total * kRec2Bytes) << 16);
+    int n_real = 0;
+    for (int gi = 0; gi < tab.n_groups; ++gi) {
+        if (lane == 0) off_out[gi] = f.off < f.pair_cap ? f.off : f.pair_cap;
+        const int seg_begin = f.off;
+        const AngularGroup grp = tab.groups[gi];
+        const int bj = sg.lo(grp.type_j), nj = sg.hi(grp.type_j) - bj;
+        const int bk = sg.lo(grp.type_k), nk = sg.hi(grp.type_k) - bk;
+        // Entries hold the type_j member's record offset in the low half and the type_k member's in the high half
+        // (same-type groups: either way).  Full 32-lane chunks of one bucket stay resident while the other bucket is
+        // swept; the chunk remainder is swept against resident chunks of the other bucket instead (few idle lanes
+        // either way); the order of the pairs is fixed, hence so is the evaluation's summation order.
+        // Gaussian screening (pantea_set_gauss_screen): reference pair = nearest neighbour of type_j with nearest of type_k
+        // (same type: the two nearest); it is a live triplet when the two are closer than the cutoff to each other, which
+        // r_j + r_k < rc guarantees.  Pairs whose weight is below exp(-T) of its weight cannot matter and are dropped.
+        f.screen = false;
+        f.r2max = 3.0e38f;
+        if (a.screen_t > 0.f && nj > 0 && nk > 0) {
+            const float eta = (float)tab.members[grp.first].eta;
+            const float reach = a.screen_t / fmaxf(eta, 1e-30f);  // T / eta
+            if (reach < 3.f * rc2f) {  // otherwise nothing inside the cutoff sphere can be dropped
+                float b1 = 3.0e38f, b2 = 3.0e38f;  // smallest r^2 of the j bucket / of the k bucket (same type: second smallest)
+                int i1 = -1, i2 = -1;
+                for (int n = lane; n < nj; n += 32) { const float v = sf4[bj + n].w; if (v < b1) { b1 = v; i1 = bj + n; } }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float v = __shfl_xor_sync(kFullMask, b1, o); const int iv = __shfl_xor_sync(kFullMask, i1, o);
+                    if (v < b1 || (v == b1 && iv < i1)) { b1 = v; i1 = iv; }
+                }
+                for (int n = lane; n < nk; n += 32) { const float v = sf4[bk + n].w; if (v < b2 && bk + n != i1) { b2 = v; i2 = bk + n; } }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float v = __shfl_xor_sync(kFullMask, b2, o); const int iv = __shfl_xor_sync(kFullMask, i2, o);
+                    if (v < b2 || (v == b2 && iv < i2)) { b2 = v; i2 = iv; }
+                }
+                if (i1 >= 0 && i2 >= 0 && sqrtf(b1) + sqrtf(b2) < 0.999f * ((float)tab.cls[grp.cls].rc)) {
+                    const float4 p1 = sf4[i1], p2 = sf4[i2];
+                    const float ex = p1.x - p2.x, ey = p1.y - p2.y, ez = p1.z - p2.z;
+                    const float ref = b1 + b2 + ex * ex + ey * ey + ez * ez;
+                    f.r2max = (ref + reach) * 1.001f + 1e-3f;
+                    f.screen = true;
+                }
+            }
+        }
+        // The work is enumerated as items (resident chunk, swept range, diagonal flag) so that the tile and emission code
+        // is instantiated once (instruction cache).
+        const bool same = grp.type_j == grp.type_k;
+        auto cost = [](int nr, int ns) { return (nr >> 5) * ns + ((nr & 31) ? ((ns + 31) >> 5) * (nr & 31) : 0); };
+        const bool res_k = same || cost(nk, nj) <= cost(nj, nk);
+        const int rb = res_k ? bk : bj, nr = res_k ? nk : nj;  // bucket whose full chunks stay resident
+        const int sb = res_k ? bj : bk, ns = res_k ? nj : nk;  // (same-type: both are the one bucket)
+        const int rshift = res_k ? 16 : 0;
+        const int full = nr >> 5, rem = nr & 31;
+        const int n_tail = rem == 0 ? 0 : (same ? full + 1 : (ns + 31) >> 5);
+        for (int it = 0; it < full + n_tail; ++it) {
+            int r0, nres, shift, s_begin, s_len;
+            bool do_diag = false;
+            if (it < full) {  // a full resident chunk: (same-type) everything before it and its own triangle, else everything
+                r0 = rb + 32 * it; nres = 32; shift = rshift; s_begin = sb; s_len = same ? 32 * it : ns; do_diag = same;
+            } else if (same) {  // remainder of the bucket: swept against the full chunks, then its own triangle
+                const int c = it - full;
+                if (c < full) { r0 = rb + 32 * c; nres = 32; shift = 16; s_begin = rb + 32 * full; s_len = rem; }
+                else { r0 = rb + 32 * full; nres = rem; shift = 16; s_begin = 0; s_len = 0; do_diag = true; }
+            } else {  // remainder of the resident bucket: swept against resident chunks of the other bucket
+                const int q = it - full;
+                r0 = sb + 32 * q; nres = min(32, ns - 32 * q); shift = 16 - rshift; s_begin = rb + 32 * full; s_len = rem;
+            }
+            if (s_len > 0) f.rect(r0, nres, shift, s_begin, s_len);
+            if (do_diag) f.diag(r0, nres);
+        }
+        n_real -= f.finish_group(pad_entry);
+        n_real += f.off - seg_begin;
+    }
+    if (lane == 0) {
+        off_out[tab.n_groups] = f.off < f.pair_cap ? f.off : f.pair_cap;
+        atomicMax(&a.flags[2], f.off);
+        if (a.counters) atomicAdd(&a.counters[3], (unsigned long long)n_real);  // list entries the evaluation will walk
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// evaluation
+// ------------------------------------------------------------------------------------------------
+// One angular group over its padded pair list.  ZM1 = zeta - 1 as a compile-time constant (0, 1, 3) or -1: runtime.
+#ifndef PANTEA_NU2
+#define PANTEA_NU2 2  // triplets per lane and loop iteration: independent dependency chains for the in-order issue
+#endif
+#ifndef PANTEA_EVAL2_MINBLOCKS
+#define PANTEA_EVAL2_MINBLOCKS 4
+#endif
+constexpr int kNU2 = PANTEA_NU2;
+
+template <int ZM1>
+__device__ __forceinline__ void angular2(const unsigned char* __restrict__ snb, const int32_t* __restrict__ list, int n_iter,
+                                         double neta, double lam, double zl, int zm1_rt, double rc, int lane, int* stage,
+                                         const double* __restrict__ etab, double& oG, double& oX, double& oY, double& oZ) {
+    constexpr int NU = kNU2;
+    const double m2_inv_rc = -2.0 / rc;
+    double aG[NU], aX[NU], aY[NU], aZ[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) { aG[u] = 0; aX[u] = 0; aY[u] = 0; aZ[u] = 0; }
+    constexpr int CH = kChunk2;  // 32-entry rows per cp.async group (a multiple of 4 and of NU)
+    const int n_chunks = (n_iter + CH - 1) / CH;
+    // every lane copies 16 bytes per 4 rows (4 x 32 entries = 512 bytes) of the chunk into the ring
+    auto stage_chunk = [&](int chunk) {
+        int* dst = stage + (chunk & 1) * (CH * 32);
+        const int32_t* src = list + (size_t)chunk * (CH * 32);
+#pragma unroll
+        for (int q = 0; q < CH / 4; ++q) cp_async16(dst + 128 * q + 4 * lane, src + 128 * q + 4 * lane);
+        cp_async_commit();
+    };
+    if (n_chunks > 0) stage_chunk(0);
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        if (chunk + 1 < n_chunks) {
+            stage_chunk(chunk + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();  // the chunk was copied by all lanes of the warp
+        const int* src = stage + (chunk & 1) * (CH * 32) + lane;
+        const int n_in = min(CH, n_iter - chunk * CH);
+        for (int i = 0; i < n_in; i += NU, src += 32 * NU) {
+            D2 j0[NU], j1[NU], j2[NU], j3[NU], k0[NU], k1[NU], k2[NU], k3[NU];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const int jk = src[32 * u];
+                const unsigned char* pj = snb + (jk & 0xffff);
+                const unsigned char* pk = snb + ((unsigned)jk >> 16);
+                // [u_x u_y | u_z r^2 | 1/r sqrt2 r | W Q]
+                j0[u] = lds128(pj); j1[u] = lds128(pj + 16); j2[u] = lds128(pj + 32); j3[u] = lds128(pj + 48);
+                k0[u] = lds128(pk); k1[u] = lds128(pk + 16); k2[u] = lds128(pk + 32); k3[u] = lds128(pk + 48);
+            }
+            double cost[NU], rjk2[NU], rjk[NU], x2[NU], th[NU], g[NU];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                cost[u] = fma(j1[u].a, k1[u].a, fma(j0[u].b, k0[u].b, j0[u].a * k0[u].a));
+                // r_jk^2 = r_j^2 + r_k^2 - 2 r_j r_k cos, kept above 1e-30 (rounding can leave zero or a negative
+                // residual for neighbours closer than 1e-7 Bohr to each other; exactly coincident ones never reach the list)
+                rjk2[u] = clamp_hi(fma(-(j2[u].b * k2[u].b), cost[u], j1[u].b + k1[u].b), 0x39b00000);
+            }
+#pragma unroll
+            for (int u = 0; u < NU; ++u) rjk[u] = sqrt_cubic(rjk2[u]);
+            // tanh(x) = 1 - 2 / (exp(2x) + 1) with 2x = 2 - 2 r_jk / rc clamped at 0: exactly 0 at and beyond the cutoff
+#pragma unroll
+            for (int u = 0; u < NU; ++u) x2[u] = clamp_hi(fma(rjk[u], m2_inv_rc, 2.0), 0);
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                th[u] = exp_tab256(x2[u], etab) + 1.0;
+                g[u] = exp_tab256(neta * rjk2[u], etab);
+            }
+#pragma unroll
+            for (int u = 0; u < NU; ++u) th[u] = fma(-2.0, rcp_cubic(th[u]), 1.0);
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const double bs = fma(lam, cost[u], 1.0);
+                double ep = (j3[u].a * k3[u].a) * ((th[u] * th[u]) * (th[u] * g[u]));
+                if (ZM1 == 1) ep *= bs;
+                else if (ZM1 == 3) ep *= bs * (bs * bs);
+                else if (ZM1 < 0) ep *= powi<double>(bs, zm1_rt);
+                const double ap = bs * ep;
+                aG[u] += ap;
+                const double Tc = zl * ep;
+                const double Bj = fma(Tc, fma(-cost[u], j2[u].a, k2[u].a), ap * j3[u].b);
+                const double Bk = fma(Tc, fma(-cost[u], k2[u].a, j2[u].a), ap * k3[u].b);
+                aX[u] = fma(Bk, k0[u].a, fma(Bj, j0[u].a, aX[u]));
+                aY[u] = fma(Bk, k0[u].b, fma(Bj, j0[u].b, aY[u]));
+                aZ[u] = fma(Bk, k1[u].a, fma(Bj, j1[u].a, aZ[u]));
+            }
+        }
+        __syncwarp();  // all lanes are done with this half of the ring before it is refilled
+    }
+#pragma unroll
+    for (int u = 1; u < NU; ++u) { aG[0] += aG[u]; aX[0] += aX[u]; aY[0] += aY[u]; aZ[0] += aZ[u]; }
+    oG = warp_sum(aG[0]); oX = warp_sum(aX[0]); oY = warp_sum(aY[0]); oZ = warp_sum(aZ[0]);
+}
+
+__global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2_MINBLOCKS) hdnnp_eval2_kernel(const AtomArgs<double> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    __shared__ double s_etab[kTab2];
+    for (int i = threadIdx.x; i < kTab2; i += blockDim.x) s_etab[i] = exp2((double)i * (1.0 / kTab2));
+    __shared__ __align__(16) int s_stage[kEvalWarps][2 * kChunk2 * 32];
+    __syncthreads();
+    const int w = blockIdx.x * kEvalWarps + wib;
+    if (w >= a.n_work) return;
+    int slot, out_row, etype;
+    if (!resolve_item(a, w, slot, out_row, etype)) return;
+    if (etype >= a.n_types) return;
+    const ElementTable& tab = a.tables[etype];
+    const int n_sf = tab.n_sf;
+    const Rec<double> ri = a.rec[slot];
+    double lx, ly, lz;
+    bool pbc;
+    item_box(a, slot, lx, ly, lz, pbc);
+
+    const int cap = a.scap;
+    const size_t per_atom = eval2_smem_bytes(cap, a.n_sf_max);
+    unsigned char* snb = smem_raw + (size_t)wib * per_atom;                    // [cap + 1] records of 80 bytes
+    double* sacc = (double*)(snb + (size_t)(cap + 1) * kRec2Bytes);           // [n_sf_max][4]
+
+    Segments sg;
+    sg.load(a.tcount + (size_t)slot * kBuckets, cap);
+    const int total = sg.total;
+    if (sg.seg[kBuckets] > cap && lane == 0) atomicMax(&a.flags[1], sg.seg[kBuckets]);
+
+    // ---- stage the neighbour block --------------------------------------------------------------------------------
+    {
+        const int32_t* row = a.nbr + (size_t)slot * a.cap;
+        const bool has_cls = tab.n_cls > 0;
+        const int ct = has_cls ? tab.cls[0].type : PANTEA_CUT_HARD;
+        const double rcc = has_cls ? tab.cls[0].rc : 1.0;
+        const double irc = rcp_cubic(rcc);
+        // phase 1 (memory): all index loads of up to five 32-neighbour rounds in flight, then all record gathers --
+        // two dependent global latencies per atom instead of two per round; the difference vectors are parked in the
+        // record slots
+        constexpr int RB = 5;
+        for (int base = 0; base < total; base += 32 * RB) {
+            int idx[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int n = base + 32 * r + lane;
+                idx[r] = row[n < total ? n : total - 1];
+            }
+            Rec<double> rr[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) rr[r] = a.rec[idx[r]];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int n = base + 32 * r + lane;
+                if (n < total) {
+                    double dx = sub_rn(ri.x, rr[r].x), dy = sub_rn(ri.y, rr[r].y), dz = sub_rn(ri.z, rr[r].z);
+                    if (pbc) { dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz); }
+                    double* p = (double*)(snb + (size_t)n * kRec2Bytes);
+                    p[0] = dx; p[1] = dy; p[2] = dz; p[3] = __hiloint2double(0, rr[r].type);
+                }
+            }
+        }
+        // phase 2 (arithmetic): every lane turns its own parked vectors into records
+        for (int n = lane; n < total; n += 32) {
+            double* p = (double*)(snb + (size_t)n * kRec2Bytes);
+            const double dx = p[0], dy = p[1], dz = p[2];
+            const int ntype = __double2loint(p[3]);
+            const double r2n = dx * dx + dy * dy + dz * dz;
+            const double iv = fast_rsqrt(r2n), r = r2n * iv;
+            double fc, q;
+            if (ct == PANTEA_CUT_TANHU) {  // tanh(x) = 1 - 2 / (exp(2x) + 1), x = 1 - r / rc
+                const double t = fma(-2.0, rcp_cubic(exp_tab256(fmax(fma(-2.0 * irc, r, 2.0), 0.0), s_etab) + 1.0), 1.0);
+                const bool in = r < rcc && t > 0.0;
+                fc = in ? t * t * t : 0.0;
+                q = in ? -3.0 * irc * (1.0 - t * t) * rcp_cubic(t) : 0.0;
+            } else {
+                double dfc;
+                cutoff_eval_ool<double>(ct, r, rcc, &fc, &dfc);
+                q = fc != 0.0 ? dfc / fc : 0.0;
+            }
+            // W = sqrt(pref) fc exp(-eta r^2), Q = fc'/fc - 2 eta r for the group this neighbour type takes part in
+            const double eta_t = tab.v2_eta[ntype], ws_t = tab.v2_wscale[ntype];
+            const double W = ws_t * fc * exp_tab256(fmax(-eta_t * r2n, -700.0), s_etab);
+            const double Q = fma(-2.0 * eta_t, r, q);
+            p[0] = dx * iv; p[1] = dy * iv; p[2] = dz * iv; p[3] = r2n; p[4] = iv; p[5] = 1.4142135623730951 * r;
+            p[6] = W; p[7] = Q; p[8] = fc; p[9] = q;
+        }
+        // the record pad entries point at: W = 0 makes every term vanish, r^2 = 1 keeps r_jk finite
+        if (lane < kRec2) ((double*)(snb + (size_t)total * kRec2Bytes))[lane] = lane == 3 ? 1.0 : 0.0;
+    }
+    __syncwarp();
+
+    // ---- radial symmetry functions (lanes over neighbours) ---------------------------------------------------------
+    for (int s = 0; s < tab.n_radial; ++s) {
+        const RadialSF sf = tab.radial[s];
+        const int lo = sg.lo(sf.type_j), hi = sg.hi(sf.type_j);
+        const double eta = sf.eta, rs = sf.r_shift;
+        double g = 0, gx = 0, gy = 0, gz = 0;
+        for (int n = lo + lane; n < hi; n += 32) {
+            const double* p = (const double*)(snb + (size_t)n * kRec2Bytes);
+            const double r = p[3] * p[4], fc = p[8], q = p[9];
+            double val, dval;
+            if (sf.kind == PANTEA_G1) { val = fc; dval = fc * q; }
+            else {
+                const double dr = r - rs, ex = fast_exp(-eta * dr * dr);
+                val = ex * fc; dval = val * (q - 2.0 * eta * dr);
+            }
+            g += val;
+            gx += dval * p[0]; gy += dval * p[1]; gz += dval * p[2];
+        }
+        g = warp_sum(g); gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
+        if (lane == 0) { double* o = sacc + 4 * sf.out; o[0] = g; o[1] = gx; o[2] = gy; o[3] = gz; }
+    }
+
+    // ---- angular symmetry functions: flat walk over the padded pair lists -------------------------------------------
+    {
+        const int32_t* offs = a.pair_off + (size_t)w * (a.max_groups + 1);
+        const int32_t* lists = a.pairs + (size_t)w * a.pair_cap;
+        int* stage = s_stage[wib];
+        for (int gi = 0; gi < tab.n_groups; ++gi) {
+            const AngularGroup grp = tab.groups[gi];
+            const AngularMember mem = tab.members[grp.first];
+            const int lo = offs[gi], n_iter = (offs[gi + 1] - lo) >> 5;
+            const double rc = tab.cls[grp.cls].rc;
+            const double zl = mem.zeta * mem.lambda0;  // pref lives in the W weights
+            double G, X, Y, Z;
+            if (mem.izeta == 1) angular2<0>(snb, lists + lo, n_iter, -mem.eta, mem.lambda0, zl, 0, rc, lane, stage, s_etab, G, X, Y, Z);
+            else if (mem.izeta == 2) angular2<1>(snb, lists + lo, n_iter, -mem.eta, mem.lambda0, zl, 1, rc, lane, stage, s_etab, G, X, Y, Z);
+            else if (mem.izeta == 4) angular2<3>(snb, lists + lo, n_iter, -mem.eta, mem.lambda0, zl, 3, rc, lane, stage, s_etab, G, X, Y, Z);
+            else angular2<-1>(snb, lists + lo, n_iter, -mem.eta, mem.lambda0, zl, mem.izeta - 1, rc, lane, stage, s_etab, G, X, Y, Z);
+            if (lane == 0) { double* o = sacc + 4 * mem.out; o[0] = G; o[1] = X; o[2] = Y; o[3] = Z; }
+        }
+    }
+    __syncwarp();
+    if (a.G)
+        for (int s = lane; s < n_sf; s += 32) a.G[(size_t)out_row * a.g_stride + s] = sacc[4 * s];
+    if (a.dG)
+        for (int e = lane; e < n_sf * 3; e += 32) {
+            const int s = e / 3, c = e - 3 * s;
+            a.dG[((size_t)out_row * a.g_stride + s) * 3 + c] = sacc[4 * s + 1 + c];
+        }
+    if (a.gbuf)
+        for (int e = lane; e < n_sf * 4; e += 32) a.gbuf[(size_t)w * a.n_sf_max * 4 + e] = sacc[e];
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------------------------
+int launch_v2(const AtomArgs<double>& a, cudaStream_t st) {
+    static size_t conf_filter[64] = {0}, conf_eval[64] = {0};
+    if (a.max_groups > 0) {
+        const size_t smem = (size_t)kFilter2Warps * ((a.scap + 32) * sizeof(float4) + kStrip2 * sizeof(int32_t));
+        int rc = opt_in_smem((const void*)pair_filter2_kernel<double>, smem, conf_filter, "pair filter: neighbour capacity too large for shared memory");
+        if (rc != PANTEA_OK) return rc;
+        const int blocks = (a.n_work + kFilter2Warps - 1) / kFilter2Warps;
+        pair_filter2_kernel<double><<<blocks, kFilter2Warps * 32, smem, st>>>(a);
+        PANTEA_LAUNCH_CHECK();
+    }
+    const size_t smem = (size_t)kEvalWarps * eval2_smem_bytes(a.scap, a.n_sf_max);
+    int rc = opt_in_smem((const void*)hdnnp_eval2_kernel, smem, conf_eval, "evaluation: neighbour capacity too large for shared memory");
+    if (rc != PANTEA_OK) return rc;
+    const int blocks = (a.n_work + kEvalWarps - 1) / kEvalWarps;
+    hdnnp_eval2_kernel<<<blocks, kEvalWarps * 32, smem, st>>>(a);
+    PANTEA_LAUNCH_CHECK();
+    return PANTEA_OK;
+}
+
+}  // namespace pantea

@@ -84,6 +84,11 @@ struct ElementTable {
     int w_off[kMaxLayers];  // offset of the layer's kernel in `weights` (bias follows the kernel)
     int n_neurons;          // sum of sizes[1..]
     const double* weights;  // device
+    // fast path of acsf2.cu: one cutoff class (tanhu), every angular group a single G3 member with integer zeta >= 1,
+    // every neighbour type in at most one group -> one (W, Q) weight pair per staged neighbour
+    int v2_ok;
+    int v2_group_of_type[kBuckets];  // the group a neighbour of this type takes part in, -1: none
+    double v2_eta[kBuckets], v2_wscale[kBuckets];  // that group's eta and sqrt(2^(1-zeta)) (0: no group)
 };
 
 }  // namespace pantea
@@ -92,6 +97,7 @@ struct pantea_potential {
     int n_elements = 0;
     double rc_max = 0.0;
     int max_sf = 0, max_cls = 1, max_neurons = 0, max_width = 0, max_members = 1, max_groups = 0;
+    bool v2_ok = true;  // every element table qualifies for the fast path of acsf2.cu
     std::vector<pantea::ElementTable> host;
     pantea::ElementTable* dev = nullptr;  // [n_elements]
     std::vector<double*> dev_weights;
@@ -168,6 +174,7 @@ struct pantea_workspace {
     int32_t* skin_flags = nullptr;  // device [4]: [0] rebuild in this call, [1] pair lists stale, [2] rebuilds, [3] skin builds
     bool skin_active = false;       // rows currently hold radius rc + skin and pos_ref matches them
     bool lists_valid = false;       // pair lists belong to the energy pass over the current rows
+    bool lists_v2 = false;          // ... and are in the fast path's format (acsf2.cu)
     struct SkinKey {
         int64_t n = -1, own_begin = 0, own_end = -1;
         double rc = 0, box[3] = {0, 0, 0};
@@ -185,6 +192,7 @@ struct pantea_workspace {
     int32_t* tmp_order = nullptr;  // [max_atoms]
     int32_t* cell_start = nullptr; // [cell_cap + 1]
     int32_t* cell_fill = nullptr;  // [cell_cap]
+    int32_t* scan_sums = nullptr;  // [cell_cap / 8192 + 1] tile sums of the two-launch cell scan
     int32_t* cell_own = nullptr;   // [cell_cap + 1] owned atoms per cell, then their exclusive scan (block-owned ranks)
     int32_t* owned_slots = nullptr; // [max_atoms] cell-ordered slots of the owned atoms, ascending
     bool owned_active = false;     // rows / evaluation run over `owned_slots` (cell mode with a proper owned range)
@@ -223,5 +231,9 @@ int neighbor_build_impl(pantea_workspace* ws, const void* pos, const int32_t* ty
 int atom_kernel_launch(pantea_workspace* ws, int element_slot, const int32_t* centres, int64_t n_centres, void* G,
                        void* dG, void* e_atom, void* forces, cudaStream_t st, int force_mode = PANTEA_FORCE_REFERENCE);
 int reduce_energy(pantea_workspace* ws, const void* e_atom, void* e_total, cudaStream_t st);
+// implemented in acsf2.cu: pair filter + evaluation of the fast path (double precision, gradients, no r_jk wrap)
+template <typename T> struct AtomArgs;
+int launch_v2(const AtomArgs<double>& a, cudaStream_t st);
 int ensure_cell_capacity(pantea_workspace* ws, int64_t ncells);
+int opt_in_smem(const void* kern, size_t smem, size_t* configured /*[64], per device*/, const char* what);
 }  // namespace pantea

@@ -141,7 +141,7 @@ static int kinetic_energy_typed(const void* vel, const void* mass, int64_t begin
 
 using namespace pantea;
 
-static double* g_ke_scratch = nullptr;  // reduction scratch for the stand-alone entry point
+static double* g_ke_scratch_dev[64] = {nullptr};  // reduction scratch of the stand-alone entry point, per device
 static const int64_t kKeScratchCap = 1 << 17;
 
 extern "C" {
@@ -198,7 +198,11 @@ int pantea_md_update_velocities(void* velocities, void* forces, const void* new_
 int pantea_md_kinetic_energy(const void* velocities, const void* masses, int64_t begin, int64_t end, double* ke_out,
                              int32_t dtype, void* stream) {
     if (!velocities || !masses || !ke_out) return fail(PANTEA_EINVAL, "pantea_md_kinetic_energy: NULL argument");
-    if (!g_ke_scratch) PANTEA_CUDA_TRY(cudaMalloc((void**)&g_ke_scratch, 8 * kKeScratchCap));
+    int dev = 0;
+    PANTEA_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(PANTEA_EINVAL, "device index out of range");
+    if (!g_ke_scratch_dev[dev]) PANTEA_CUDA_TRY(cudaMalloc((void**)&g_ke_scratch_dev[dev], 8 * kKeScratchCap));
+    double* g_ke_scratch = g_ke_scratch_dev[dev];
     if (dtype == PANTEA_F64)
         return kinetic_energy_typed<double>(velocities, masses, begin, end, g_ke_scratch, kKeScratchCap, ke_out, (cudaStream_t)stream);
     return kinetic_energy_typed<float>(velocities, masses, begin, end, g_ke_scratch, kKeScratchCap, ke_out, (cudaStream_t)stream);

@@ -66,59 +66,95 @@ __global__ void cell_assign_kernel(const T* __restrict__ pos, int n, CellArg ca,
     atomicAdd(&cell_count[c], 1);
 }
 
-// exclusive scan of counts[0..n) into start[0..n] by one block; also zeroes `fill`
-__global__ void cell_scan_kernel(const int32_t* counts, int n, int32_t* start, int32_t* fill,
-                                 const int32_t* __restrict__ guard) {  // counts may alias start or fill (in place)
+// Exclusive scan of counts[0..n) into start[0..n] (start[n] = total); also zeroes `fill`.  Two launches: every block
+// of 1024 threads sums its tile of 8192 cells, then every block scans its own tile behind the sum of the tiles before
+// it (a single block took 38 us for the 3 x 10^4 half-width cells of the 10^5-atom box).  counts may alias start or
+// fill: a thread reads all of its inputs before it writes its outputs, and the tile sums are complete before any write.
+constexpr int kScanThreads = 1024, kScanK = 8, kScanTile = kScanThreads * kScanK;
+
+__global__ void __launch_bounds__(kScanThreads) cell_tile_sums_kernel(const int32_t* __restrict__ counts, int n,
+                                                                      int32_t* __restrict__ tile_sums,
+                                                                      const int32_t* __restrict__ guard) {
     if (guard && *guard == 0) return;
     __shared__ int warp_sums[32];
-    __shared__ int carry_s;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthreads = blockDim.x;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    constexpr int K = 8;  // consecutive cells per thread: the half-width grid has ~10x the cells of the coarse one
-    for (int base = 0; base < n; base += nthreads * K) {
-        const int i0 = base + tid * K;
-        int v[K];
-        int x = 0;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int i0 = blockIdx.x * kScanTile + tid * kScanK;
+    int x = 0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            v[k] = i0 + k < n ? counts[i0 + k] : 0;  // all inputs of the thread are read before its outputs are written
-            x += v[k];
-        }
-        const int mine = x;
+    for (int k = 0; k < kScanK; ++k) x += i0 + k < n ? counts[i0 + k] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+    if (lane == 0) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int w = warp_sums[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(kFull, w, o);
+        if (lane == 0) tile_sums[blockIdx.x] = w;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) cell_scan_kernel(const int32_t* counts, int n, const int32_t* __restrict__ tile_sums,
+                                                                 int32_t* start, int32_t* fill, const int32_t* __restrict__ guard) {
+    if (guard && *guard == 0) return;
+    __shared__ int warp_sums[32];
+    __shared__ int base_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // sum of the tiles before this one (a few dozen values at most: one warp)
+    if (wid == 0) {
+        int b = 0;
+        for (int t = lane; t < (int)blockIdx.x; t += 32) b += tile_sums[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(kFull, b, o);
+        if (lane == 0) base_s = b;
+    }
+    const int i0 = blockIdx.x * kScanTile + tid * kScanK;
+    int v[kScanK];
+    int x = 0;
+#pragma unroll
+    for (int k = 0; k < kScanK; ++k) {
+        v[k] = i0 + k < n ? counts[i0 + k] : 0;
+        x += v[k];
+    }
+    const int mine = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(kFull, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int w = warp_sums[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int y = __shfl_up_sync(kFull, x, o);
-            if (lane >= o) x += y;
+            const int y = __shfl_up_sync(kFull, w, o);
+            if (lane >= o) w += y;
         }
-        if (lane == 31) warp_sums[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            int w = lane < (nthreads >> 5) ? warp_sums[lane] : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int y = __shfl_up_sync(kFull, w, o);
-                if (lane >= o) w += y;
-            }
-            warp_sums[lane] = w;
-        }
-        __syncthreads();
-        int carry = carry_s;
-        int incl = x + (wid > 0 ? warp_sums[wid - 1] : 0) + carry;
-        int run = incl - mine;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if (i0 + k < n) {
-                start[i0 + k] = run;
-                fill[i0 + k] = 0;
-            }
-            run += v[k];
-        }
-        __syncthreads();
-        if (tid == nthreads - 1) carry_s = incl;
-        __syncthreads();
+        warp_sums[lane] = w;
     }
-    if (tid == 0) start[n] = carry_s;
+    __syncthreads();
+    const int incl = x + (wid > 0 ? warp_sums[wid - 1] : 0) + base_s;
+    int run = incl - mine;
+#pragma unroll
+    for (int k = 0; k < kScanK; ++k) {
+        if (i0 + k < n) {
+            start[i0 + k] = run;
+            fill[i0 + k] = 0;
+        }
+        run += v[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == kScanThreads - 1) start[n] = incl;
+}
+
+static int launch_cell_scan(pantea_workspace* ws, const int32_t* counts, int n, int32_t* start, int32_t* fill,
+                            const int32_t* guard, cudaStream_t st) {
+    const int tiles = (n + kScanTile - 1) / kScanTile;
+    cell_tile_sums_kernel<<<tiles, kScanThreads, 0, st>>>(counts, n, ws->scan_sums, guard);
+    PANTEA_LAUNCH_CHECK();
+    cell_scan_kernel<<<tiles, kScanThreads, 0, st>>>(counts, n, ws->scan_sums, start, fill, guard);
+    PANTEA_LAUNCH_CHECK();
+    return PANTEA_OK;
 }
 
 __global__ void cell_scatter_kernel(const int32_t* __restrict__ cell_of, int n, const int32_t* __restrict__ cell_start,
@@ -691,8 +727,8 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
         }
         cell_assign_kernel<T><<<blocks_n, threads, 0, st>>>(pos, (int)n, ca, ba, ws->cell_of, ws->cell_fill, ws->wide_flag, guard);
         PANTEA_LAUNCH_CHECK();
-        cell_scan_kernel<<<1, 1024, 0, st>>>(ws->cell_fill, (int)ncells, ws->cell_start, ws->cell_fill, guard);
-        PANTEA_LAUNCH_CHECK();
+        rcode = launch_cell_scan(ws, ws->cell_fill, (int)ncells, ws->cell_start, ws->cell_fill, guard, st);
+        if (rcode != PANTEA_OK) return rcode;
         cell_scatter_kernel<<<blocks_n, threads, 0, st>>>(ws->cell_of, (int)n, ws->cell_start, ws->cell_fill, ws->tmp_order, guard);
         PANTEA_LAUNCH_CHECK();
         const int blocks_c = (int)((ncells * 32 + threads - 1) / threads);
@@ -702,8 +738,8 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
                                                                own_lo, own_hi, owned ? ws->cell_own : nullptr, ws->nbr_tcount);
         PANTEA_LAUNCH_CHECK();
         if (owned) {  // compact list of the owned atoms' slots (cell order): scan of the per-cell counts, then fill
-            cell_scan_kernel<<<1, 1024, 0, st>>>(ws->cell_own, (int)ncells, ws->cell_own, ws->cell_fill, guard);
-            PANTEA_LAUNCH_CHECK();
+            rcode = launch_cell_scan(ws, ws->cell_own, (int)ncells, ws->cell_own, ws->cell_fill, guard, st);
+            if (rcode != PANTEA_OK) return rcode;
             owned_fill_kernel<T><<<blocks_c, threads, 0, st>>>(rec, ws->cell_start, (int)ncells, ws->cell_own, own_lo, own_hi,
                                                                ws->owned_slots, guard);
             PANTEA_LAUNCH_CHECK();
@@ -795,8 +831,11 @@ int pantea_neighbor_status(pantea_workspace* ws, int32_t* max_count, void* strea
     }
     const int seen = h[0] > h[1] ? h[0] : h[1];  // maxima since the last status call (0: nothing was built since)
     if (seen > 0 && h[0] <= ws->cap) {
-        // shared-memory footprint of the evaluation kernels follows the observed maximum (+10 % + 8 head-room)
+        // shared-memory footprint of the evaluation kernels follows the observed maximum (+10 % + 8 head-room); the fast
+        // path keeps four blocks of four 80-byte-record neighbour blocks per SM only up to 144 staged neighbours, so
+        // the head-room gives way down to 8 there
         int want = (seen + seen / 10 + 8 + 7) / 8 * 8;
+        if (ws->pot && ws->pot->v2_ok && want > 144 && seen + 8 <= 144) want = 144;
         if (want < 32) want = 32;
         if (want > ws->cap) want = ws->cap;
         // sized from the first observation, afterwards it only grows: shrinking on a later, smaller observation would

@@ -80,6 +80,25 @@ static int build_table(const pantea_element_desc& d, int n_elements, int e, Elem
         }
     }
     (void)n_members; (void)e;
+    // fast-path eligibility (acsf2.cu)
+    t.v2_ok = 1;
+    for (int b = 0; b < kBuckets; ++b) { t.v2_group_of_type[b] = -1; t.v2_eta[b] = 0.0; t.v2_wscale[b] = 0.0; }
+    if (t.n_cls > 1) t.v2_ok = 0;
+    if (t.n_cls == 1 && t.cls[0].type != PANTEA_CUT_TANHU && t.n_groups > 0) t.v2_ok = 0;
+    for (int g = 0; g < t.n_groups && t.v2_ok; ++g) {
+        const AngularGroup& grp = t.groups[g];
+        const AngularMember& mem = t.members[grp.first];
+        if (grp.count != 1 || grp.kind != PANTEA_G3 || mem.izeta < 1 || mem.izeta > 16 || !(mem.eta >= 0.0) ||
+            !(mem.eta * t.cls[grp.cls].rc * t.cls[grp.cls].rc * 1.01 < 690.0)) { t.v2_ok = 0; break; }
+        for (int side = 0; side < 2; ++side) {
+            const int ty = side == 0 ? grp.type_j : grp.type_k;
+            if (side == 1 && grp.type_k == grp.type_j) break;
+            if (t.v2_group_of_type[ty] >= 0) t.v2_ok = 0;  // a neighbour type in two groups needs two weight pairs
+            t.v2_group_of_type[ty] = g;
+            t.v2_eta[ty] = mem.eta;
+            t.v2_wscale[ty] = std::sqrt(mem.pref);
+        }
+    }
     // scaler
     t.has_scaler = (d.scale_shift && d.scale_slope && d.scale_offset) ? 1 : 0;
     for (int s = 0; s < d.n_symfunc; ++s) {
@@ -157,6 +176,7 @@ int pantea_potential_create(const pantea_potential_desc* desc, pantea_potential*
         if (t.n_cls > pot->max_cls) pot->max_cls = t.n_cls;
         for (int g = 0; g < t.n_groups; ++g) if (t.groups[g].count > pot->max_members) pot->max_members = t.groups[g].count;
         if (t.n_groups > pot->max_groups) pot->max_groups = t.n_groups;
+        if (!t.v2_ok) pot->v2_ok = false;
         if (t.n_neurons > pot->max_neurons) pot->max_neurons = t.n_neurons;
         for (int l = 0; l <= t.n_layers; ++l)
             if (t.n_layers > 0 && t.sizes[l] > pot->max_width) pot->max_width = t.sizes[l];
@@ -248,7 +268,7 @@ int pantea_workspace_destroy(pantea_workspace* ws) {
     if (ws->capture_stream) cudaStreamDestroy(ws->capture_stream);
     void* ptrs[] = {ws->rec, ws->slot_of, ws->struct_of, ws->nbr, ws->nbr_tcount, ws->cell_of, ws->tmp_order,
                     ws->cell_start, ws->cell_fill, ws->flags, ws->e_partial, ws->md_forces, ws->md_eatom, ws->md_ke,
-                    ws->pairs, ws->pair_off, ws->gbuf, ws->wbuf, ws->rec_screen, ws->wide_flag, ws->pos_ref, ws->skin_flags, ws->owned_slots, ws->cell_own};
+                    ws->pairs, ws->pair_off, ws->gbuf, ws->wbuf, ws->scan_sums, ws->rec_screen, ws->wide_flag, ws->pos_ref, ws->skin_flags, ws->owned_slots, ws->cell_own};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete ws;
@@ -294,11 +314,13 @@ int ensure_cell_capacity(pantea_workspace* ws, int64_t ncells) {
     if (ws->cell_start) cudaFree(ws->cell_start);
     if (ws->cell_fill) cudaFree(ws->cell_fill);
     if (ws->cell_own) cudaFree(ws->cell_own);
-    ws->cell_start = ws->cell_fill = ws->cell_own = nullptr;
+    if (ws->scan_sums) cudaFree(ws->scan_sums);
+    ws->cell_start = ws->cell_fill = ws->cell_own = ws->scan_sums = nullptr;
     ws->cell_cap = 0;
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_start, 4 * (ncells + 1)));
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_fill, 4 * (ncells + 1)));
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_own, 4 * (ncells + 1)));
+    PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->scan_sums, 4 * (ncells / 8192 + 2)));
     ws->cell_cap = ncells;
     ws->skin_active = false;  // fresh (unzeroed) binning scratch: the next build is a forced one
     ++ws->arg_epoch;

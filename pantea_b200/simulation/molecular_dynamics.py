@@ -92,7 +92,9 @@ class MDSimulator:
         ws = dev.workspace(s.natoms, s.dtype, engine.number_density(s))
         types = engine.remap_types(s, dev.type_of).contiguous()
         box = engine.box_lengths(s)
-        # capacity check once up front (the loop itself never synchronises)
+        # capacity check up front; the device loop itself never synchronises, so it runs in chunks with a capacity check
+        # between them: a chunk during which a neighbour row, the staged block or a pair list overflowed is repeated
+        # from its saved start state after the capacities have been raised (a densifying box needs this on long runs)
         ws.bind(s.positions, types, box, dev.r_cutoff)
         pos = s.positions.clone().contiguous()
         vel = system.velocities.clone().contiguous()
@@ -104,12 +106,29 @@ class MDSimulator:
                                thermo.time_constant if thermo else 0.0, units.BOLTZMANN_CONSTANT,
                                1 if record else 0, 1 if use_graph else 0, 1 if self.mass_scaled else 0,
                                1 if self.forces == "full" else 0)
-        _lib.check(_lib.load().pantea_md_run(ws.handle, _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(frc), _lib.ptr(mass),
-                                             _lib.ptr(types), s.natoms, _lib.box_arg(box), int(num_steps),
-                                             C.byref(params), _lib.ptr(scalars), _lib.stream_ptr()))
-        ws._keep = (pos, types)
-        mx = C.c_int32(0)
-        _lib.check(_lib.load().pantea_neighbor_status(ws.handle, C.byref(mx), _lib.stream_ptr()))
+        lib = _lib.load()
+        chunk = int(self.check_every) if getattr(self, "check_every", 0) else 100
+        done = 0
+        while done < num_steps:
+            todo = min(chunk, num_steps - done)
+            saved = (pos.clone(), vel.clone(), frc.clone())
+            for attempt in range(6):
+                out = scalars[done:done + todo] if record else None
+                _lib.check(lib.pantea_md_run(ws.handle, _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(frc), _lib.ptr(mass),
+                                             _lib.ptr(types), s.natoms, _lib.box_arg(box), int(todo),
+                                             C.byref(params), _lib.ptr(out), _lib.stream_ptr()))
+                ws._keep = (pos, types)
+                mx = C.c_int32(0)
+                code = lib.pantea_neighbor_status(ws.handle, C.byref(mx), _lib.stream_ptr())
+                if code != _lib.PANTEA_ECAPACITY:
+                    _lib.check(code)
+                    break
+                if attempt == 5:
+                    _lib.check(code)
+                if mx.value > (ws.max_neighbors + 31) // 32 * 32:  # a neighbour row overflowed: only a larger workspace helps
+                    ws._grow(mx.value)
+                pos.copy_(saved[0]); vel.copy_(saved[1]); frc.copy_(saved[2])
+            done += todo
         s.positions, system.velocities, s.forces = pos, vel, frc
         self.step += num_steps
         self.elapsed_time += num_steps * float(self.time_step)
