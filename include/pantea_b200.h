@@ -275,6 +275,39 @@ int pantea_halo_pack(const void* positions /*[n,3]*/, const int64_t* send_idx, i
 int pantea_halo_unpack_add(void* out /*[n_own,3]*/, const void* recv_buf /*[n_send,3]*/, const int64_t* order,
                            const int64_t* first, int64_t n_own, int32_t dtype, void* stream);
 
+/* -- brick-decomposed MD over NVLink peer memory ("3-D spatial bricks, ghost shell width = rc, forward
+      halo of ghost positions, atom migration"; the reference is single-process: atoms/structure.py:45-49 only mentions
+      the idea).  One process per GPU.  Atoms keep their global index on every rank; a rank owns the atoms inside its
+      brick and holds ghost copies of those within r_cutoff of it.  Per step: ONE kernel integrates the owned atoms and
+      stores their new positions straight into the mailbox rows of every rank that needs them (st.global on CUDA-IPC
+      mapped peer pointers = NVLink writes; migrating atoms take their velocity and force rows along) and publishes the
+      step number; ONE kernel waits for all peers' step numbers and unpacks; then the single-GPU pipeline runs on the
+      present atoms (global cell grid: per-atom results do not depend on the number of ranks); then the velocity
+      update.  Captured once as a CUDA graph; no collective library call and no host synchronisation inside.
+      dims[3] = bricks per axis (product = world, rank = (ix*py+iy)*pz+iz), cuts_d = the dims[d]-1 interior boundaries
+      (HOST, ascending; NULL when dims[d] == 1), own_cap = upper bound of the atoms one rank may own (launch grids).
+      Integrator = the reference's (no mass, no thermostat: NVE). */
+typedef struct pantea_mgpu pantea_mgpu;
+int pantea_mgpu_create(pantea_workspace* ws, int32_t rank, int32_t world, int64_t n_atoms, const double* box,
+                       const int32_t* dims, const double* cuts_x, const double* cuts_y, const double* cuts_z,
+                       double r_cutoff, double dt, int64_t own_cap, pantea_mgpu** out);
+/* peer mapping: every rank exports pantea_mgpu_handle_bytes() bytes (a cudaIpcMemHandle_t), the caller gathers them in
+   rank order (HOST) and hands the concatenation to pantea_mgpu_connect (world == 1: connected at creation) */
+int64_t pantea_mgpu_handle_bytes(void);
+int pantea_mgpu_export_handle(pantea_mgpu* mg, void* handle_out);
+int pantea_mgpu_connect(pantea_mgpu* mg, const void* all_handles);
+/* (re)start from full-length replicated DEVICE arrays positions / velocities [n,3] (same on every rank; types [n] is
+   borrowed for the lifetime of the runs) and compute the owned atoms' forces.  The caller puts a barrier (all ranks
+   idle) before and after this call. */
+int pantea_mgpu_set_state(pantea_mgpu* mg, const void* positions, const void* velocities, const int32_t* types, void* stream);
+int pantea_mgpu_run(pantea_mgpu* mg, int64_t n_steps, int32_t use_graph, void* stream);
+/* copies of the rank's full-length arrays (any may be NULL): positions are valid where roles >= 1, velocities / forces
+   where roles == 2 (0 absent, 1 ghost, 2 owned).  *status (HOST, may be NULL; synchronises): 0 ok, 1 + r = peer r never
+   published a step within the spin limit, 1000 = own_cap exceeded. */
+int pantea_mgpu_read(pantea_mgpu* mg, void* positions, void* velocities, void* forces, uint8_t* roles, int32_t* status,
+                     void* stream);
+int pantea_mgpu_destroy(pantea_mgpu* mg);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,15 @@ PROTOTYPES = {
     "pantea_scaler_stats": (C.c_int, [_VP, _I64, _I64, _I64, _I32, _VP, _VP]),
     "pantea_halo_pack": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _I64, C.POINTER(_DBL), _DBL, _VP, _I32, _VP]),
     "pantea_halo_unpack_add": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _VP]),
+    "pantea_mgpu_create": (C.c_int, [_VP, _I32, _I32, _I64, C.POINTER(_DBL), C.POINTER(_I32), C.POINTER(_DBL),
+                                     C.POINTER(_DBL), C.POINTER(_DBL), _DBL, _DBL, _I64, C.POINTER(_VP)]),
+    "pantea_mgpu_handle_bytes": (_I64, []),
+    "pantea_mgpu_export_handle": (C.c_int, [_VP, _VP]),
+    "pantea_mgpu_connect": (C.c_int, [_VP, _VP]),
+    "pantea_mgpu_set_state": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "pantea_mgpu_run": (C.c_int, [_VP, _I64, _I32, _VP]),
+    "pantea_mgpu_read": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.POINTER(_I32), _VP]),
+    "pantea_mgpu_destroy": (C.c_int, [_VP]),
 }
 
 _lib: Optional[C.CDLL] = None

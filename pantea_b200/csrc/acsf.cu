@@ -915,6 +915,12 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
     a.own_begin = (int)ws->own_begin; a.own_end = ws->own_end < 0 ? (int)ws->n : (int)ws->own_end;
     a.owned_slots = energy_pass && ws->owned_active ? ws->owned_slots : nullptr;
     a.n_work = energy_pass ? (a.owned_slots ? a.own_end - a.own_begin : (int)ws->n) : (int)n_centres;
+    a.n_work_dev = nullptr;
+    if (ws->role) {  // brick decomposition: owned atoms by role, their number on the device
+        if (!energy_pass || !ws->owned_active) return fail(PANTEA_EINVAL, "role-owned workspaces only run the energy / force pass");
+        a.n_work = (int)ws->own_cap;
+        a.n_work_dev = ws->cell_own + (int64_t)ws->ncell[0] * ws->ncell[1] * ws->ncell[2];
+    }
     a.pairs = ws->pairs; a.pair_off = ws->pair_off; a.pair_cap = ws->pair_cap; a.max_groups = pot->max_groups;
     a.G = (T*)G; a.dG = (T*)dG; a.e_atom = (T*)e_atom; a.forces = (T*)forces;
     a.gbuf = nullptr;

@@ -55,6 +55,7 @@ struct AtomArgs {
     int by_slot;  // 1: work item = cell-sorted slot (energy/force pass); 0: work item = centre list entry
     int own_begin, own_end;
     const int32_t* owned_slots;  // by_slot passes of a block-owned rank: work item -> slot (NULL: work item = slot)
+    const int32_t* n_work_dev;   // role mode (brick decomposition): number of work items on the device, n_work is its bound
     // pair lists written by the filter, read by the evaluation
     int32_t* pairs;      // [n_work][pair_cap]  (j | k << 16), row positions within the staged neighbour block
     int32_t* pair_off;   // [n_work][max_groups + 1] offsets of each group's segment
@@ -117,9 +118,10 @@ __device__ __forceinline__ void group_sync(int atom_in_block) {
 template <typename T>
 __device__ __forceinline__ bool resolve_item(const AtomArgs<T>& a, int w, int& slot, int& out_row, int& etype) {
     if (a.by_slot) {
+        if (a.n_work_dev && w >= *a.n_work_dev) return false;
         slot = a.owned_slots ? a.owned_slots[w] : w;
         out_row = rec_idx(a.rec[slot]);
-        if (out_row < a.own_begin || out_row >= a.own_end) return false;
+        if (!a.n_work_dev && (out_row < a.own_begin || out_row >= a.own_end)) return false;
     } else {
         const int oi = a.centres ? a.centres[w] : w;
         slot = a.slot_of[oi];

@@ -12,7 +12,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
-SOURCES = ["potential.cu", "neighbor.cu", "acsf.cu", "acsf2.cu", "md.cu", "microbench.cu", "lj.cu", "scaler.cu", "halo.cu"]
+SOURCES = ["potential.cu", "neighbor.cu", "acsf.cu", "acsf2.cu", "md.cu", "microbench.cu", "lj.cu", "scaler.cu", "halo.cu", "mgpu.cu"]
 HEADERS = [HERE / "internal.cuh", HERE / "math.cuh", HERE / "acsf_common.cuh", ROOT / "include" / "pantea_b200.h"]
 LIB = HERE.parent / "libpantea_b200.so"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -163,6 +163,10 @@ struct pantea_workspace {
     const int32_t* struct_ptr = nullptr;  // borrowed (batch mode)
     const double* boxes = nullptr;        // borrowed (batch mode)
     int64_t own_begin = 0, own_end = -1;  // -1: all atoms
+    // brick-decomposed multi-GPU engine (mgpu.cu): per-atom role instead of an index range -- 0 absent on this rank
+    // (not binned), 1 ghost, 2 owned; the owned count is then only known on the device (cell_own[ncells])
+    const uint8_t* role = nullptr;  // borrowed, [n]
+    int64_t own_cap = 0;            // static upper bound of the owned atoms (launch grids)
 
     // device buffers
     void* rec = nullptr;           // Rec<T>[max_atoms]

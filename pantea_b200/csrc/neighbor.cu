@@ -47,10 +47,11 @@ __device__ __forceinline__ int cell_coord(double x, double inv, int n) {
 template <typename T>
 __global__ void cell_assign_kernel(const T* __restrict__ pos, int n, CellArg ca, BoxArg box, int32_t* __restrict__ cell_of,
                                    int32_t* __restrict__ cell_count, int32_t* __restrict__ wide_flag,
-                                   const int32_t* __restrict__ guard) {
+                                   const int32_t* __restrict__ guard, const uint8_t* __restrict__ role) {
     if (guard && *guard == 0) return;  // Verlet skin: the rows of the last rebuild are still valid
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (role && role[i] == 0) { cell_of[i] = -1; return; }  // not on this rank (brick decomposition)
     {   // the screening pass measures true minimum-image distances; they equal the reference's single-shift ones only
         // while every coordinate difference stays below 1.5 box lengths
         const double x = (double)pos[3 * i], y = (double)pos[3 * i + 1], z = (double)pos[3 * i + 2];
@@ -164,6 +165,7 @@ __global__ void cell_scatter_kernel(const int32_t* __restrict__ cell_of, int n, 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int c = cell_of[i];
+    if (c < 0) return;
     int p = cell_start[c] + atomicAdd(&cell_fill[c], 1);
     tmp_order[p] = i;
 }
@@ -176,8 +178,9 @@ __global__ void cell_sort_pack_kernel(const T* __restrict__ pos, const int32_t* 
                                       int32_t* __restrict__ slot_of, Rec<float>* __restrict__ rec_screen, BoxArg box,
                                       int32_t* __restrict__ cell_fill, const int32_t* __restrict__ guard,
                                       int own_begin, int own_end, int32_t* __restrict__ cell_own,
-                                      int32_t* __restrict__ tcount) {
+                                      int32_t* __restrict__ tcount, const uint8_t* __restrict__ role) {
     if (guard && *guard == 0) return;
+    auto is_owned = [&](int idx) { return role ? role[idx] == 2 : (idx >= own_begin && idx < own_end); };
     int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (cell >= ncells) return;
@@ -187,7 +190,7 @@ __global__ void cell_sort_pack_kernel(const T* __restrict__ pos, const int32_t* 
         int owned = 0;
         for (int a = lo + lane; a < hi; a += 32) {
             const int idx = tmp_order[a];
-            owned += (idx >= own_begin && idx < own_end) ? 1 : 0;
+            owned += is_owned(idx) ? 1 : 0;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) owned += __shfl_xor_sync(kFull, owned, o);
@@ -202,7 +205,7 @@ __global__ void cell_sort_pack_kernel(const T* __restrict__ pos, const int32_t* 
         rec_set(r, bucket_of(types[mine], n_types), mine);
         rec[lo + rank] = r;
         slot_of[mine] = lo + rank;
-        if (cell_own && !(mine >= own_begin && mine < own_end))  // no row is built for it: report zero neighbours
+        if (cell_own && !is_owned(mine))  // no row is built for it: report zero neighbours
             for (int b = 0; b < kBuckets; ++b) tcount[(size_t)(lo + rank) * kBuckets + b] = 0;
         if (rec_screen) {  // box-wrapped coordinates in [0, L], rounded to float
             const double x = (double)r.x, y = (double)r.y, z = (double)r.z;
@@ -220,7 +223,8 @@ __global__ void cell_sort_pack_kernel(const T* __restrict__ pos, const int32_t* 
 template <typename T>
 __global__ void owned_fill_kernel(const Rec<T>* __restrict__ rec, const int32_t* __restrict__ cell_start, int ncells,
                                   const int32_t* __restrict__ own_start, int own_begin, int own_end,
-                                  int32_t* __restrict__ owned_slots, const int32_t* __restrict__ guard) {
+                                  int32_t* __restrict__ owned_slots, const int32_t* __restrict__ guard,
+                                  const uint8_t* __restrict__ role) {
     if (guard && *guard == 0) return;
     int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -232,7 +236,7 @@ __global__ void owned_fill_kernel(const Rec<T>* __restrict__ rec, const int32_t*
         bool mine = false;
         if (s < hi) {
             const int idx = rec_idx(rec[s]);
-            mine = idx >= own_begin && idx < own_end;
+            mine = role ? role[idx] == 2 : (idx >= own_begin && idx < own_end);
         }
         const unsigned m = __ballot_sync(kFull, mine);
         if (mine) owned_slots[out + __popc(m & ((1u << lane) - 1u))] = s;
@@ -286,6 +290,8 @@ struct RowArgs {
     const int32_t* guard;          // Verlet skin: skip the kernel while *guard == 0 (NULL: always run)
     const int32_t* owned_slots;    // block-owned ranks: the warps walk this compact slot list (NULL: every slot)
     int n_owned;
+    const int32_t* n_owned_dev;    // role mode: the owned count lives on the device (NULL: n_owned)
+    const uint8_t* role;           // role mode: every slot of the owned list is owned
 };
 
 template <typename T, int MODE>
@@ -294,12 +300,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PANTEA_ROWS_MINBLOCKS) ne
     if (a.guard && *a.guard == 0) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int w = blockIdx.x * kWarpsPerBlock + wib;
-    if (w >= (a.owned_slots ? a.n_owned : a.n)) return;
+    if (w >= (a.owned_slots ? (a.n_owned_dev ? *a.n_owned_dev : a.n_owned) : a.n)) return;
     const int i = a.owned_slots ? a.owned_slots[w] : w;
     int32_t* L = smem_rows + wib * a.cap;
     const Rec<T> ri = rec[i];
     const int oi = rec_idx(ri);
-    if (oi < a.own_begin || oi >= a.own_end) {
+    if (!a.role && (oi < a.own_begin || oi >= a.own_end)) {
         if (lane < kBuckets) a.tcount[(size_t)i * kBuckets + lane] = 0;
         return;
     }
@@ -714,7 +720,9 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
     ws->skin_active = use_skin;
     if (!use_skin) ws->lists_valid = false;
     const int own_lo = (int)ws->own_begin, own_hi = ws->own_end < 0 ? (int)n : (int)ws->own_end;
-    const bool owned = use_cells && (own_lo > 0 || own_hi < (int)n);
+    const uint8_t* role = ws->role;
+    if (role && !use_cells) return fail(PANTEA_EINVAL, "brick decomposition needs a box of at least three cells per axis");
+    const bool owned = use_cells && (role != nullptr || own_lo > 0 || own_hi < (int)n);
     ws->owned_active = owned;
     if (use_cells) {
         const int64_t ncells = (int64_t)ca.nx * ca.ny * ca.nz;
@@ -725,7 +733,7 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
             PANTEA_CUDA_TRY(cudaMemsetAsync(ws->cell_fill, 0, 4 * (ncells + 1), st));
             PANTEA_CUDA_TRY(cudaMemsetAsync(ws->wide_flag, 0, 4, st));
         }
-        cell_assign_kernel<T><<<blocks_n, threads, 0, st>>>(pos, (int)n, ca, ba, ws->cell_of, ws->cell_fill, ws->wide_flag, guard);
+        cell_assign_kernel<T><<<blocks_n, threads, 0, st>>>(pos, (int)n, ca, ba, ws->cell_of, ws->cell_fill, ws->wide_flag, guard, role);
         PANTEA_LAUNCH_CHECK();
         rcode = launch_cell_scan(ws, ws->cell_fill, (int)ncells, ws->cell_start, ws->cell_fill, guard, st);
         if (rcode != PANTEA_OK) return rcode;
@@ -735,13 +743,13 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
         cell_sort_pack_kernel<T><<<blocks_c, threads, 0, st>>>(pos, types, ws->n_types, ws->cell_start, (int)ncells,
                                                                ws->tmp_order, rec, ws->slot_of,
                                                                (Rec<float>*)ws->rec_screen, ba, ws->cell_fill, guard,
-                                                               own_lo, own_hi, owned ? ws->cell_own : nullptr, ws->nbr_tcount);
+                                                               own_lo, own_hi, owned ? ws->cell_own : nullptr, ws->nbr_tcount, role);
         PANTEA_LAUNCH_CHECK();
         if (owned) {  // compact list of the owned atoms' slots (cell order): scan of the per-cell counts, then fill
             rcode = launch_cell_scan(ws, ws->cell_own, (int)ncells, ws->cell_own, ws->cell_fill, guard, st);
             if (rcode != PANTEA_OK) return rcode;
             owned_fill_kernel<T><<<blocks_c, threads, 0, st>>>(rec, ws->cell_start, (int)ncells, ws->cell_own, own_lo, own_hi,
-                                                               ws->owned_slots, guard);
+                                                               ws->owned_slots, guard, role);
             PANTEA_LAUNCH_CHECK();
         }
     } else {
@@ -760,14 +768,16 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
     ra.wide_flag = ws->wide_flag;
     ra.guard = guard;
     ra.owned_slots = owned ? ws->owned_slots : nullptr;
-    ra.n_owned = own_hi - own_lo;
+    ra.n_owned = role ? (int)ws->own_cap : own_hi - own_lo;
+    ra.n_owned_dev = role ? ws->cell_own + (int64_t)ca.nx * ca.ny * ca.nz : nullptr;
+    ra.role = role;
     {   // error bound of the screening distance (see neighbor_rows_kernel): per-axis |error| <= 5 L 2^-24, squared
         // distance |error| <= 2 sqrt(3) r delta + 3 delta^2 + 4 2^-24 r^2 at r ~ rc; doubled for safety
         const double lmax = std::max(ws->box[0], std::max(ws->box[1], ws->box[2]));
         const double delta = 5.0 * lmax * 5.9604644775390625e-08;
         ra.screen_band = (float)(2.0 * (3.5 * rc * delta + 3.0 * delta * delta + 3.0e-7 * rc * rc));
     }
-    const int blocks_w = (int)(((owned ? (int64_t)(own_hi - own_lo) : n) + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const int blocks_w = (int)(((owned ? (int64_t)ra.n_owned : n) + kWarpsPerBlock - 1) / kWarpsPerBlock);
     const size_t smem = (size_t)kWarpsPerBlock * ws->cap * sizeof(int32_t);
     if (use_cells)
         neighbor_rows_kernel<T, kModeCell><<<blocks_w, kWarpsPerBlock * 32, smem, st>>>(rec, ra);
