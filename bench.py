@@ -50,6 +50,10 @@ def parse_args():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="diagnostics only: skip the oracle comparison before timing")
+    ap.add_argument("--engine", default="brick", choices=["brick", "replicated"],
+                    help="brick (default): spatial bricks, ghost positions pushed into the peers' mailboxes over NVLink by "
+                         "the integration kernel, CUDA-graph steps (csrc/mgpu.cu); replicated: round-1 scheme, all "
+                         "positions all-gathered with NCCL every step")
     ap.add_argument("--skin", type=float, default=0.0,
                     help="Verlet skin (Bohr) of the secondary measurement `verlet_skin`; 0 skips it")
     ap.add_argument("--kernel-times", action="store_true",
@@ -135,11 +139,18 @@ def parity_check(md, lib, _lib, pos_h, types_h, box_h, dtype, rank, world, dev):
     import torch.distributed as dist
 
     n = len(pos_h)
-    frc = md.gather_owned(md.frc).double()
-    counts = torch.zeros(n, dtype=torch.int32, device=dev)
     own = torch.zeros(n, dtype=torch.int32, device=dev)
     _lib.check(lib.pantea_neighbor_counts(md.ws.handle, _lib.ptr(own), _lib.stream_ptr()))
-    counts[md.lo:md.hi] = own[md.lo:md.hi]
+    one_owner = True
+    if hasattr(md, "gather"):  # brick engine: owned rows by role
+        _, _, frc, owners = md.gather()
+        frc = frc.double()
+        one_owner = bool((owners == 1).all())
+        counts = torch.where(md.read()[3] == 2, own, torch.zeros_like(own))
+    else:
+        frc = md.gather_owned(md.frc).double()
+        counts = torch.zeros(n, dtype=torch.int32, device=dev)
+        counts[md.lo:md.hi] = own[md.lo:md.hi]
     if world > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     out = None
@@ -162,8 +173,9 @@ def parity_check(md, lib, _lib, pos_h, types_h, box_h, dtype, rank, world, dev):
         n_equal = bool((counts.cpu().numpy() == np.diff(row_ptr).astype(np.int32)).all())
         out = {"n_atoms": n, "max_err_over_tol": over, "rtol": rtol, "criterion": "|dF| <= rtol*(|F|+rms(F)) per component",
                "max_rel_F": rel, "max_abs_dF": float(err.max()), "rms_F": rms, "neighbors_equal": n_equal,
+               "one_owner_per_atom": one_owner,
                "oracle": f"all {n} atoms, oracle/hdnnp_oracle.c, {threads} threads, {cpu_s:.1f} s",
-               "ok": bool(over <= 1.0 and n_equal)}
+               "ok": bool(over <= 1.0 and n_equal and one_owner)}
     flag = torch.tensor([0.0 if (out is None or out["ok"]) else 1.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MAX)
@@ -258,7 +270,12 @@ def run_b200(args) -> None:
     n = len(pos_h)
     box = [float(b) for b in box_h]
     t = lambda a, dt=dtype: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)  # noqa: E731
-    md = ReplicatedMD(pot, t(pos_h), t(vel_h), t(mass_h), t(types_h, torch.int32), box, DT, rank, world)
+    brick = args.engine == "brick"
+    if brick:
+        from pantea_b200.brick import BrickMD
+        md = BrickMD(pot, t(pos_h), t(vel_h), t(types_h, torch.int32), box, DT, rank, world)
+    else:
+        md = ReplicatedMD(pot, t(pos_h), t(vel_h), t(mass_h), t(types_h, torch.int32), box, DT, rank, world)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def flush():
@@ -275,7 +292,7 @@ def run_b200(args) -> None:
     # and the per-atom work drifts.  To keep the workload stationary for any K, the timed steps replay SEGMENT-step
     # pieces of the trajectory from the initial state (the reset is outside the timed events).  The untimed warm-up
     # runs one full segment, which also sizes the pair-list / shared-memory capacities for everything that follows.
-    pos0, vel0 = md.pos.clone(), md.vel.clone()
+    pos0, vel0 = t(pos_h), t(vel_h)
     max_seen = 0
 
     def capacity_ok(m=None) -> bool:
@@ -345,6 +362,21 @@ def run_b200(args) -> None:
     if not capacity_ok():
         raise SystemExit("bench.py: a capacity flag was raised inside the timed region; the measurement is void")
     max_seen_main = max_seen
+    engine_info = None
+    if brick:
+        own = torch.tensor([float(md.owned_count())], dtype=torch.float64, device=dev)
+        own_max = own.clone()
+        all_reduce_max(own_max)
+        engine_info = {"bricks": list(md.grid.dims), "owned_atoms_max_over_ranks": int(own_max.item()),
+                       "own_cap": int(md.own_cap), "halo": "ghost positions stored by the integration kernel into the "
+                       "peers' mailboxes (CUDA IPC over NVLink), step-number flags, no collective call in the step"}
+        brick_md = md
+        # the diagnostics below (roofline counters, e2e through pantea_neighbor_build / pantea_energy_forces with host
+        # buffers) use a plain index-range-owned workspace of the same size
+        md = ReplicatedMD(pot, t(pos_h), t(vel_h), t(mass_h), t(types_h, torch.int32), box, DT, rank, world)
+        for _ in range(2):
+            md.step()
+        capacity_ok(md)
 
     # ---- secondary measurement: the same K steps with Verlet-skin reuse of rows and pair lists ------------------
     # (the headline above rebuilds the neighbour rows every step, like the reference; this one is reported beside it)
@@ -417,25 +449,43 @@ def run_b200(args) -> None:
     roofline = None
     extra = {}
     if rank == 0:
+        # work units of one force evaluation: the generic kernels count the live units of the reference algorithm
+        # (pairs, radial-SF and triplet-SF evaluations); the fast path reports the pair-list entries it actually walks
+        # (Gaussian screening drops triplets whose weight is below 4e-18 of the group's largest)
         counters = torch.zeros(4, dtype=torch.int64, device=dev)
         _lib.check(lib.pantea_workspace_set_counters(md.ws.handle, _lib.ptr(counters)))
+        lib.pantea_set_fast_path(0)
+        md._forces(md.frc_new)
+        lib.pantea_set_fast_path(1)
         md._forces(md.frc_new)
         torch.cuda.synchronize()
         _lib.check(lib.pantea_workspace_set_counters(md.ws.handle, None))
-        n_pair, n_rad, n_trip = (int(x) for x in counters[:3].tolist())
+        n_pair, n_rad, n_trip, n_walked = (int(x) for x in counters[:4].tolist())
+        fast_path = n_walked > 0
         n_own = md.hi - md.lo
         own_types = types_h[md.lo:md.hi]
-        flops_kernel = (FLOP_PAIR * n_pair + FLOP_RAD * n_rad + FLOP_TRIP * n_trip
-                        + sum(FLOP_MLP[int(x)] for x in own_types))
+        flops_mlp = sum(FLOP_MLP[int(x)] for x in own_types)
+        flops_reference = FLOP_PAIR * n_pair + FLOP_RAD * n_rad + FLOP_TRIP * n_trip            # SURVEY 8(d) convention
+        flops_executed = FLOP_PAIR * n_pair + FLOP_RAD * n_rad + FLOP_TRIP * (n_walked if fast_path else n_trip)
         reps = 5
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        eval_ms = []
+        if fast_path:
+            _lib.check(lib.pantea_eval_timing(1, None))
         for a, b in ev:
             flush()
             a.record()
             md._forces(md.frc_new)
             b.record()
+            if fast_path:
+                ms_k = C.c_float(0.0)
+                _lib.check(lib.pantea_eval_timing(1, C.byref(ms_k)))
+                eval_ms.append(ms_k.value)
         torch.cuda.synchronize()
+        if fast_path:
+            _lib.check(lib.pantea_eval_timing(0, None))
         k_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+        dom_ms = statistics.mean(eval_ms) if eval_ms else k_ms
         # measured FMA-pipe peak (the bound of this kernel; MEASURED_PEAKS.json only holds HBM and bf16 tensor peaks)
         scratch = torch.zeros(16, dtype=torch.float64, device=dev)
         fl = C.c_double(0.0)
@@ -447,21 +497,33 @@ def run_b200(args) -> None:
             b.record()
             torch.cuda.synchronize()
             peak = max(peak, fl.value / (a.elapsed_time(b) * 1e-3) / 1e12)
-        achieved = flops_kernel / (k_ms * 1e-3) / 1e12
         traffic = None
         tfile = ROOT / "profiles" / "traffic.json"
         if tfile.exists():
             try:
-                traffic = json.loads(tfile.read_text()).get("force_eval_dram_bytes_per_launch")
+                traffic = json.loads(tfile.read_text()).get("eval_kernel_dram_bytes_per_launch")
             except (ValueError, OSError):
                 traffic = None
+        achieved = flops_reference / (dom_ms * 1e-3) / 1e12
         roofline = {"bound": "fp64_pipe" if dtype == torch.float64 else "fp32_pipe",
-                    "kernel": "force evaluation = pair_filter_kernel + hdnnp_eval_kernel (dominant, ~74 %) + mlp_force_kernel",
+                    "kernel": ("hdnnp_eval2_kernel (dominant kernel: neighbour records, radial and angular symmetry functions "
+                               "with central gradients)" if fast_path else
+                               "force evaluation = pair_filter_kernel + hdnnp_eval_kernel + mlp_force_kernel"),
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak if peak else None, "traffic": traffic,
-                    "peak_source": "measured live: FMA microbenchmark (pantea_bench_fma), CUDA-core pipe",
-                    "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops_kernel,
-                    "units_per_launch": {"atoms": n_own, "pairs": n_pair, "radial_sf": n_rad, "triplet_sf": n_trip}}
+                    "what": "achieved = ALGORITHMIC flops of the reference algorithm (SURVEY 8(d): 74/pair + 39/radial SF + "
+                            "160/live triplet SF) / CUDA-event duration of the kernel; frac_executed counts only the triplets "
+                            "the kernel walks after Gaussian screening",
+                    "frac_executed": flops_executed / (dom_ms * 1e-3) / 1e12 / peak if peak else None,
+                    "peak_source": "measured live: FMA microbenchmark (pantea_bench_fma), CUDA-core pipe; "
+                                   "MEASURED_PEAKS.json holds no FP64 figure",
+                    "kernel_ms": dom_ms, "algorithmic_flops_per_launch": flops_reference,
+                    "executed_flops_per_launch": flops_executed,
+                    "units_per_launch": {"atoms": n_own, "pairs": n_pair, "radial_sf": n_rad, "triplet_sf": n_trip,
+                                         "triplet_sf_walked": n_walked if fast_path else n_trip},
+                    "force_evaluation": {"what": "pair filter + evaluation + network kernels (everything but the neighbour rows)",
+                                         "ms": k_ms, "algorithmic_flops": flops_reference + flops_mlp,
+                                         "frac": (flops_reference + flops_mlp) / (k_ms * 1e-3) / 1e12 / peak if peak else None}}
         extra["kernel_share_of_step"] = k_ms / (ms_total / args.steps)
         peaks_file = ROOT / "MEASURED_PEAKS.json"
         if peaks_file.exists():
@@ -525,7 +587,10 @@ def run_b200(args) -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": workload_name(n), "atoms": n, "parallelism": f"replicated-coords block-owned x{world}",
+            "config": {"workload": workload_name(n), "atoms": n,
+                       "parallelism": (f"brick-decomposed x{world} {tuple(engine_info['bricks'])}, ghost halo over NVLink peer memory"
+                                       if brick else f"replicated-coords block-owned x{world}"),
+                       "engine": engine_info,
                        "l2": "flushed between timed steps (256 MB write)" if not args.no_flush else "not flushed",
                        "max_neighbors_seen": int(mx.value), "force_mode": "reference (central-role gradient)",
                        "trajectory": f"timed steps replay {SEGMENT}-step segments from the initial state (untimed reset)"},

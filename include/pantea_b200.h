@@ -237,8 +237,14 @@ int pantea_bench_fma(int32_t dtype, int32_t iters, int32_t blocks, int32_t threa
                      void* stream);
 /* overwrite `bytes` (> L2 capacity) of DEVICE scratch so that the following kernel sees a cold L2 */
 int pantea_l2_flush(void* scratch, int64_t bytes, void* stream);
+/* enable != 0: bracket every later launch of the specialised evaluation kernel (the dominant kernel of the step) with
+   CUDA events on its own stream; *ms (HOST, may be NULL) = duration of the most recent bracketed launch.  Eager
+   launches only (not inside graph capture). */
+int pantea_eval_timing(int32_t enable, float* ms);
 /* optional work counters, DEVICE uint64[4] or NULL: [0] neighbour pairs, [1] radial-SF evaluations,
-   [2] triplet-SF evaluations -- accumulated by every later descriptor / energy launch of `ws` */
+   [2] triplet-SF evaluations (generic kernels: live triplets of the reference algorithm), [3] pair-list entries the
+   specialised evaluation walks (after Gaussian screening, without padding) -- accumulated by every later descriptor /
+   energy launch of `ws` */
 int pantea_workspace_set_counters(pantea_workspace* ws, void* counters);
 
 /* Verlet-skin reuse of the neighbour rows and pair lists (the reference notes the missing

@@ -617,6 +617,9 @@ __global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2_MINBLOCKS) hdnnp
 // ------------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------------
+static int g_time_eval = 0;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+
 int launch_v2(const AtomArgs<double>& a, cudaStream_t st) {
     static size_t conf_filter[64] = {0}, conf_eval[64] = {0};
     if (a.max_groups > 0) {
@@ -631,9 +634,32 @@ int launch_v2(const AtomArgs<double>& a, cudaStream_t st) {
     int rc = opt_in_smem((const void*)hdnnp_eval2_kernel, smem, conf_eval, "evaluation: neighbour capacity too large for shared memory");
     if (rc != PANTEA_OK) return rc;
     const int blocks = (a.n_work + kEvalWarps - 1) / kEvalWarps;
+    if (g_time_eval) {  // measurement hook (pantea_eval_timing): CUDA events around the dominant kernel, not capturable
+        if (!g_ev0) { PANTEA_CUDA_TRY(cudaEventCreate(&g_ev0)); PANTEA_CUDA_TRY(cudaEventCreate(&g_ev1)); }
+        PANTEA_CUDA_TRY(cudaEventRecord(g_ev0, st));
+    }
     hdnnp_eval2_kernel<<<blocks, kEvalWarps * 32, smem, st>>>(a);
     PANTEA_LAUNCH_CHECK();
+    if (g_time_eval) PANTEA_CUDA_TRY(cudaEventRecord(g_ev1, st));
     return PANTEA_OK;
 }
 
 }  // namespace pantea
+
+extern "C" {
+
+// bench.py: enable != 0 brackets every later launch of the fast path's evaluation kernel with CUDA events on its stream;
+// *ms (HOST, may be NULL) receives the duration of the most recent bracketed launch (synchronises on it).  Returns
+// PANTEA_EINVAL when no launch has been bracketed yet.  Not usable inside stream capture.
+int pantea_eval_timing(int32_t enable, float* ms) {
+    using namespace pantea;
+    if (ms) {
+        if (!g_ev0 || !g_ev1) return fail(PANTEA_EINVAL, "pantea_eval_timing: no bracketed launch yet");
+        PANTEA_CUDA_TRY(cudaEventSynchronize(g_ev1));
+        PANTEA_CUDA_TRY(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+    }
+    g_time_eval = enable ? 1 : 0;
+    return PANTEA_OK;
+}
+
+}  // extern "C"

@@ -197,7 +197,8 @@ struct pantea_workspace {
     int32_t* cell_start = nullptr; // [cell_cap + 1]
     int32_t* cell_fill = nullptr;  // [cell_cap]
     int32_t* scan_sums = nullptr;  // [cell_cap / 8192 + 1] tile sums of the two-launch cell scan
-    int32_t* cell_own = nullptr;   // [cell_cap + 1] owned atoms per cell, then their exclusive scan (block-owned ranks)
+    int32_t* cell_own = nullptr;   // [cell_cap + 1] exclusive scan of the owned atoms per cell (ranks that own a part)
+    int32_t* cell_own_cnt = nullptr;  // [cell_cap + 1] owned atoms per cell (counted while binning, zeroed by the scan)
     int32_t* owned_slots = nullptr; // [max_atoms] cell-ordered slots of the owned atoms, ascending
     bool owned_active = false;     // rows / evaluation run over `owned_slots` (cell mode with a proper owned range)
     int64_t cell_cap = 0;

@@ -66,8 +66,8 @@ __device__ __forceinline__ int brick_owner(const BrickTable& b, double x, double
 // periodic distance of coordinate x to the interval [lo, hi) along an axis of length L (0 inside)
 __device__ __forceinline__ double axis_gap(double x, double lo, double hi, double L) {
     if (x >= lo && x < hi) return 0.0;
-    double a = lo - x; a -= L * floor(a / L);  // forward distance to the lower edge
-    double c = x - hi; c -= L * floor(c / L);  // backward distance to the upper edge
+    double a = lo - x; if (a < 0.0) a += L;  // forward distance to the lower edge (x is wrapped: |lo - x| < L)
+    double c = x - hi; if (c < 0.0) c += L;  // backward distance to the upper edge
     return a < c ? a : c;
 }
 __device__ __forceinline__ bool in_shell(const BrickTable& b, int r, double x, double y, double z) {
@@ -136,10 +136,11 @@ __global__ void mgpu_integrate_push_kernel(int n, const uint8_t* __restrict__ ro
             }
         }
     }
-    // publish: every thread's stores are ordered before the block's ticket, the last block raises the flags
-    __threadfence_system();
+    // publish: the block's stores are ordered before its ticket (barrier, then one cumulative system-scope fence), the
+    // last block raises the flags
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned int t = atomicAdd(done, 1u);
         if (t == gridDim.x - 1) {
             *done = 0;
@@ -200,7 +201,7 @@ __global__ void mgpu_velocities_kernel(int n, const uint8_t* __restrict__ role, 
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *epoch_p += 1;
-        if (*n_owned > own_cap) atomicExch(err, 1000);  // more owned atoms than the launch grids cover: results invalid
+        if (n_owned && *n_owned > own_cap) atomicExch(err, 1000);  // more owned atoms than the launch grids cover: results invalid
     }
 }
 
@@ -280,9 +281,9 @@ int mgpu_step_typed(pantea_mgpu* mg, cudaStream_t st) {
     rc = atom_kernel_launch(mg->ws, -1, nullptr, 0, nullptr, nullptr, nullptr, mg->frc_new, st, PANTEA_FORCE_REFERENCE);
     if (rc) return rc;
     const pantea_workspace* ws = mg->ws;
+    const int32_t* n_owned = ws->role ? ws->cell_own + (int64_t)ws->ncell[0] * ws->ncell[1] * ws->ncell[2] : nullptr;
     mgpu_velocities_kernel<T><<<blocks, threads, 0, st>>>(n, mg->role, mg->bt_dev, mg->pt_dev, (const T*)mg->frc_new, (T)mg->dt,
-                                                          mg->epoch, ws->cell_own + (int64_t)ws->ncell[0] * ws->ncell[1] * ws->ncell[2],
-                                                          (int)ws->own_cap, mg->err);
+                                                          mg->epoch, n_owned, (int)ws->own_cap, mg->err);
     PANTEA_LAUNCH_CHECK();
     return PANTEA_OK;
 }
@@ -341,7 +342,7 @@ int pantea_mgpu_create(pantea_workspace* ws, int32_t rank, int32_t world, int64_
     }
     // rows and evaluation run over the owned atoms only; their number is known on the device, `own_cap` bounds it for
     // the launch grids (exceeding it raises the error status)
-    ws->role = mg->role;
+    ws->role = world > 1 ? mg->role : nullptr;  // one rank owns every atom: the plain single-GPU pipeline
     ws->own_cap = own_cap > 0 && own_cap < n_atoms ? own_cap : n_atoms;
     ws->own_begin = 0; ws->own_end = -1;
     ++ws->arg_epoch;
@@ -477,7 +478,7 @@ int pantea_mgpu_read(pantea_mgpu* mg, void* positions, void* velocities, void* f
 
 int pantea_mgpu_destroy(pantea_mgpu* mg) {
     if (!mg) return PANTEA_OK;
-    if (mg->ws && mg->ws->role == mg->role) { mg->ws->role = nullptr; mg->ws->own_cap = 0; ++mg->ws->arg_epoch; }
+    if (mg->ws && (mg->ws->role == mg->role || mg->world == 1)) { mg->ws->role = nullptr; mg->ws->own_cap = 0; ++mg->ws->arg_epoch; }
     if (mg->graph) cudaGraphExecDestroy(mg->graph);
     if (mg->capture_stream) cudaStreamDestroy(mg->capture_stream);
     for (int r = 0; r < mg->world; ++r)

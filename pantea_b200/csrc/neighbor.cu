@@ -47,7 +47,8 @@ __device__ __forceinline__ int cell_coord(double x, double inv, int n) {
 template <typename T>
 __global__ void cell_assign_kernel(const T* __restrict__ pos, int n, CellArg ca, BoxArg box, int32_t* __restrict__ cell_of,
                                    int32_t* __restrict__ cell_count, int32_t* __restrict__ wide_flag,
-                                   const int32_t* __restrict__ guard, const uint8_t* __restrict__ role) {
+                                   const int32_t* __restrict__ guard, const uint8_t* __restrict__ role,
+                                   int32_t* __restrict__ own_count, int own_begin, int own_end) {
     if (guard && *guard == 0) return;  // Verlet skin: the rows of the last rebuild are still valid
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -65,6 +66,8 @@ __global__ void cell_assign_kernel(const T* __restrict__ pos, int n, CellArg ca,
     int c = (cz * ca.ny + cy) * ca.nx + cx;
     cell_of[i] = c;
     atomicAdd(&cell_count[c], 1);
+    // owned atoms per cell (ranks that own a part of the atoms): scanned together with the cell counts
+    if (own_count && (role ? role[i] == 2 : (i >= own_begin && i < own_end))) atomicAdd(&own_count[c], 1);
 }
 
 // Exclusive scan of counts[0..n) into start[0..n] (start[n] = total); also zeroes `fill`.  Two launches: every block
@@ -75,8 +78,10 @@ constexpr int kScanThreads = 1024, kScanK = 8, kScanTile = kScanThreads * kScanK
 
 __global__ void __launch_bounds__(kScanThreads) cell_tile_sums_kernel(const int32_t* __restrict__ counts, int n,
                                                                       int32_t* __restrict__ tile_sums,
-                                                                      const int32_t* __restrict__ guard) {
+                                                                      const int32_t* __restrict__ guard,
+                                                                      const int32_t* __restrict__ counts_b) {
     if (guard && *guard == 0) return;
+    if (blockIdx.y == 1) { counts = counts_b; tile_sums += gridDim.x; }  // second scan of the same launch
     __shared__ int warp_sums[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int i0 = blockIdx.x * kScanTile + tid * kScanK;
@@ -96,8 +101,10 @@ __global__ void __launch_bounds__(kScanThreads) cell_tile_sums_kernel(const int3
 }
 
 __global__ void __launch_bounds__(kScanThreads) cell_scan_kernel(const int32_t* counts, int n, const int32_t* __restrict__ tile_sums,
-                                                                 int32_t* start, int32_t* fill, const int32_t* __restrict__ guard) {
+                                                                 int32_t* start, int32_t* fill, const int32_t* __restrict__ guard,
+                                                                 const int32_t* counts_b, int32_t* start_b, int32_t* fill_b) {
     if (guard && *guard == 0) return;
+    if (blockIdx.y == 1) { counts = counts_b; start = start_b; fill = fill_b; tile_sums += gridDim.x; }
     __shared__ int warp_sums[32];
     __shared__ int base_s;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -148,12 +155,14 @@ __global__ void __launch_bounds__(kScanThreads) cell_scan_kernel(const int32_t* 
     if (blockIdx.x == gridDim.x - 1 && tid == kScanThreads - 1) start[n] = incl;
 }
 
+// scans counts -> start (zeroing fill) and, when counts_b is given, counts_b -> start_b (zeroing fill_b) in the same launches
 static int launch_cell_scan(pantea_workspace* ws, const int32_t* counts, int n, int32_t* start, int32_t* fill,
-                            const int32_t* guard, cudaStream_t st) {
+                            const int32_t* counts_b, int32_t* start_b, int32_t* fill_b, const int32_t* guard, cudaStream_t st) {
     const int tiles = (n + kScanTile - 1) / kScanTile;
-    cell_tile_sums_kernel<<<tiles, kScanThreads, 0, st>>>(counts, n, ws->scan_sums, guard);
+    const dim3 grid(tiles, counts_b ? 2 : 1);
+    cell_tile_sums_kernel<<<grid, kScanThreads, 0, st>>>(counts, n, ws->scan_sums, guard, counts_b);
     PANTEA_LAUNCH_CHECK();
-    cell_scan_kernel<<<tiles, kScanThreads, 0, st>>>(counts, n, ws->scan_sums, start, fill, guard);
+    cell_scan_kernel<<<grid, kScanThreads, 0, st>>>(counts, n, ws->scan_sums, start, fill, guard, counts_b, start_b, fill_b);
     PANTEA_LAUNCH_CHECK();
     return PANTEA_OK;
 }
@@ -186,16 +195,6 @@ __global__ void cell_sort_pack_kernel(const T* __restrict__ pos, const int32_t* 
     if (cell >= ncells) return;
     if (lane == 0) cell_fill[cell] = 0;  // leave the counting-sort scratch zeroed for the next (device-decided) rebuild
     int lo = cell_start[cell], hi = cell_start[cell + 1];
-    if (cell_own) {  // block-owned ranks: owned atoms of this cell (their slots are compacted by owned_fill_kernel)
-        int owned = 0;
-        for (int a = lo + lane; a < hi; a += 32) {
-            const int idx = tmp_order[a];
-            owned += is_owned(idx) ? 1 : 0;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) owned += __shfl_xor_sync(kFull, owned, o);
-        if (lane == 0) cell_own[cell] = owned;
-    }
     for (int a = lo + lane; a < hi; a += 32) {
         int mine = tmp_order[a];
         int rank = 0;
@@ -731,11 +730,14 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
         ws->mode = kModeCell;
         if (!guard || forced) {  // device-decided rebuilds find the scratch zeroed by the previous rebuild's kernels
             PANTEA_CUDA_TRY(cudaMemsetAsync(ws->cell_fill, 0, 4 * (ncells + 1), st));
+            if (owned) PANTEA_CUDA_TRY(cudaMemsetAsync(ws->cell_own_cnt, 0, 4 * (ncells + 1), st));
             PANTEA_CUDA_TRY(cudaMemsetAsync(ws->wide_flag, 0, 4, st));
         }
-        cell_assign_kernel<T><<<blocks_n, threads, 0, st>>>(pos, (int)n, ca, ba, ws->cell_of, ws->cell_fill, ws->wide_flag, guard, role);
+        cell_assign_kernel<T><<<blocks_n, threads, 0, st>>>(pos, (int)n, ca, ba, ws->cell_of, ws->cell_fill, ws->wide_flag, guard, role,
+                                                            owned ? ws->cell_own_cnt : nullptr, own_lo, own_hi);
         PANTEA_LAUNCH_CHECK();
-        rcode = launch_cell_scan(ws, ws->cell_fill, (int)ncells, ws->cell_start, ws->cell_fill, guard, st);
+        rcode = launch_cell_scan(ws, ws->cell_fill, (int)ncells, ws->cell_start, ws->cell_fill,
+                                 owned ? ws->cell_own_cnt : nullptr, ws->cell_own, ws->cell_own_cnt, guard, st);
         if (rcode != PANTEA_OK) return rcode;
         cell_scatter_kernel<<<blocks_n, threads, 0, st>>>(ws->cell_of, (int)n, ws->cell_start, ws->cell_fill, ws->tmp_order, guard);
         PANTEA_LAUNCH_CHECK();
@@ -745,9 +747,7 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
                                                                (Rec<float>*)ws->rec_screen, ba, ws->cell_fill, guard,
                                                                own_lo, own_hi, owned ? ws->cell_own : nullptr, ws->nbr_tcount, role);
         PANTEA_LAUNCH_CHECK();
-        if (owned) {  // compact list of the owned atoms' slots (cell order): scan of the per-cell counts, then fill
-            rcode = launch_cell_scan(ws, ws->cell_own, (int)ncells, ws->cell_own, ws->cell_fill, guard, st);
-            if (rcode != PANTEA_OK) return rcode;
+        if (owned) {  // compact list of the owned atoms' slots (cell order) behind the scanned per-cell owned counts
             owned_fill_kernel<T><<<blocks_c, threads, 0, st>>>(rec, ws->cell_start, (int)ncells, ws->cell_own, own_lo, own_hi,
                                                                ws->owned_slots, guard, role);
             PANTEA_LAUNCH_CHECK();

@@ -268,7 +268,7 @@ int pantea_workspace_destroy(pantea_workspace* ws) {
     if (ws->capture_stream) cudaStreamDestroy(ws->capture_stream);
     void* ptrs[] = {ws->rec, ws->slot_of, ws->struct_of, ws->nbr, ws->nbr_tcount, ws->cell_of, ws->tmp_order,
                     ws->cell_start, ws->cell_fill, ws->flags, ws->e_partial, ws->md_forces, ws->md_eatom, ws->md_ke,
-                    ws->pairs, ws->pair_off, ws->gbuf, ws->wbuf, ws->scan_sums, ws->rec_screen, ws->wide_flag, ws->pos_ref, ws->skin_flags, ws->owned_slots, ws->cell_own};
+                    ws->pairs, ws->pair_off, ws->gbuf, ws->wbuf, ws->scan_sums, ws->cell_own_cnt, ws->rec_screen, ws->wide_flag, ws->pos_ref, ws->skin_flags, ws->owned_slots, ws->cell_own};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete ws;
@@ -315,12 +315,15 @@ int ensure_cell_capacity(pantea_workspace* ws, int64_t ncells) {
     if (ws->cell_fill) cudaFree(ws->cell_fill);
     if (ws->cell_own) cudaFree(ws->cell_own);
     if (ws->scan_sums) cudaFree(ws->scan_sums);
-    ws->cell_start = ws->cell_fill = ws->cell_own = ws->scan_sums = nullptr;
+    if (ws->cell_own_cnt) cudaFree(ws->cell_own_cnt);
+    ws->cell_start = ws->cell_fill = ws->cell_own = ws->scan_sums = ws->cell_own_cnt = nullptr;
     ws->cell_cap = 0;
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_start, 4 * (ncells + 1)));
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_fill, 4 * (ncells + 1)));
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_own, 4 * (ncells + 1)));
-    PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->scan_sums, 4 * (ncells / 8192 + 2)));
+    PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->scan_sums, 4 * 2 * (ncells / 8192 + 2)));
+    PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_own_cnt, 4 * (ncells + 1)));
+    PANTEA_CUDA_TRY(cudaMemset(ws->cell_own_cnt, 0, 4 * (ncells + 1)));
     ws->cell_cap = ncells;
     ws->skin_active = false;  // fresh (unzeroed) binning scratch: the next build is a forced one
     ++ws->arg_epoch;
