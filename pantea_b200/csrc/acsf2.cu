@@ -171,7 +171,9 @@ struct Filter2 {
 
     // resident chunk (lanes hold staged neighbours r0 + lane, lane < nres; their record offset goes into the entry half
     // selected by res_shift) against the swept range [s_begin, s_begin + ns): tiles of 32 broadcast reads
-    __device__ __forceinline__ void rect(int r0, int nres, int res_shift, int s_begin, int ns) {
+    // tri: resident chunk and swept range are the same neighbours -- only the pairs with the swept index below the
+    // resident one are kept (lower triangle of the tile)
+    __device__ __forceinline__ void rect(int r0, int nres, int res_shift, int s_begin, int ns, bool tri = false) {
         const float4 fl = sf4[r0 + (lane < nres ? lane : 0)];
         const bool l_ok = lane < nres && (!cls_test || fl.w < rc2f);
         const int res_part = ((r0 + lane) * kRec2Bytes) << res_shift;
@@ -196,6 +198,7 @@ struct Filter2 {
             if (nb < 32) mask &= (1u << nb) - 1u;
             if (cls_test) mask &= __ballot_sync(kFullMask, lane < nb && sf4[s_begin + s0 + lane].w < rc2f);
             if (!l_ok) mask = 0;
+            if (tri) mask &= (1u << lane) - 1u;
             emit<false>(mask, nb, res_part + (((s_begin + s0) * kRec2Bytes) << (16 - res_shift)), stride, 0, 0);
         }
     }
@@ -361,7 +364,11 @@ __global__ void __launch_bounds__(kFilter2Warps * 32, PANTEA_FILTER2_MINBLOCKS) 
                 r0 = sb + 32 * q; nres = min(32, ns - 32 * q); shift = 16 - rshift; s_begin = rb + 32 * full; s_len = rem;
             }
             if (s_len > 0) f.rect(r0, nres, shift, s_begin, s_len);
+#ifdef PANTEA_FILTER2_WRAP_DIAG
             if (do_diag) f.diag(r0, nres);
+#else
+            if (do_diag && nres > 1) f.rect(r0, nres, 16, r0, nres, true);  // the chunk's own triangle: a masked tile
+#endif
         }
         n_real -= f.finish_group(pad_entry);
         n_real += f.off - seg_begin;

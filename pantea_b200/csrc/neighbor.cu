@@ -289,6 +289,7 @@ struct RowArgs {
     const int32_t* guard;          // Verlet skin: skip the kernel while *guard == 0 (NULL: always run)
     const int32_t* owned_slots;    // block-owned ranks: the warps walk this compact slot list (NULL: every slot)
     int n_owned;
+    int tmp_cap;                   // per-warp scratch entries behind the row lists (0: none)
     const int32_t* n_owned_dev;    // role mode: the owned count lives on the device (NULL: n_owned)
     const uint8_t* role;           // role mode: every slot of the owned list is owned
 };
@@ -386,7 +387,101 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PANTEA_ROWS_MINBLOCKS) ne
         if (screen) scan_screen(lo, hi); else scan(lo, hi);
     };
 
-    if (MODE == kModeCell && a.cell.r == 2) {
+    if (MODE == kModeCell && a.cell.r == 2 && screen && a.tmp_cap > 0) {
+        // Half-width cells, 5 x 5 x 5 stencil.  Lane r < 25 owns the (dy, dz) stencil row r and writes the slots of its
+        // candidates into its stretch of a per-warp scratch list; the flattened list -- in exactly the order of the scan
+        // below (dz outer, dy inner, wrapped x-part first, slots ascending) -- is then walked by all 32 lanes with one
+        // shared-memory read per candidate instead of a five-step shuffle search.  The x-range of a row is
+        // clipped to the cells that can hold an atom within the list radius given the row's (dy, dz) offset and the
+        // atom's position inside its own cell: a dropped cell lies farther than rc in the periodic metric, hence also
+        // in the reference's single-shift metric, so the accepted set does not change.
+        const int nx = a.cell.nx, ny = a.cell.ny, nz = a.cell.nz;
+        const double ux = (double)ri.x * a.cell.inv_x, uy = (double)ri.y * a.cell.inv_y, uz = (double)ri.z * a.cell.inv_z;
+        const double fx0 = floor(ux), fy0 = floor(uy), fz0 = floor(uz);
+        const int cx = cell_coord((double)ri.x, a.cell.inv_x, nx);
+        const int cy = cell_coord((double)ri.y, a.cell.inv_y, ny);
+        const int cz = cell_coord((double)ri.z, a.cell.inv_z, nz);
+        int a0 = 0, la = 0, b0 = 0, lb = 0;
+        if (lane < 25) {
+            const int oz = lane / 5 - 2, oy = lane % 5 - 2;
+            int z = cz + oz, y = cy + oy;
+            z = z < 0 ? z + nz : (z >= nz ? z - nz : z);
+            y = y < 0 ? y + ny : (y >= ny ? y - ny : y);
+            // smallest possible |dy|, |dz| to any point of the row's cells (in length units)
+            const double gy = oy == 0 ? 0.0 : (oy > 0 ? (double)oy - (uy - fy0) : (uy - fy0) - (double)(oy + 1)) / a.cell.inv_y;
+            const double gz = oz == 0 ? 0.0 : (oz > 0 ? (double)oz - (uz - fz0) : (uz - fz0) - (double)(oz + 1)) / a.cell.inv_z;
+            const double budget = a.rc * a.rc * (1.0 + 1e-9) - gy * gy - gz * gz;
+            if (budget >= 0.0) {
+                const double hx = (sqrt(budget) + 1e-9 * a.rc) * a.cell.inv_x;  // reach along x in cell units
+                int xlo = (int)floor(ux - hx) - (int)fx0, xhi = (int)floor(ux + hx) - (int)fx0;  // relative to the own cell
+                xlo = xlo < -2 ? -2 : xlo; xhi = xhi > 2 ? 2 : xhi;
+                xlo += cx; xhi += cx;
+                const int rowc = (z * ny + y) * nx;
+                if (xlo >= 0 && xhi < nx) {
+                    a0 = a.cell_start[rowc + xlo]; la = a.cell_start[rowc + xhi + 1] - a0;
+                } else if (xlo < 0) {  // cells xlo + nx .. nx - 1, then 0 .. xhi
+                    a0 = a.cell_start[rowc + xlo + nx]; la = a.cell_start[rowc + nx] - a0;
+                    b0 = a.cell_start[rowc]; lb = a.cell_start[rowc + xhi + 1] - b0;
+                } else {               // cells xlo .. nx - 1, then 0 .. xhi - nx
+                    a0 = a.cell_start[rowc + xlo]; la = a.cell_start[rowc + nx] - a0;
+                    b0 = a.cell_start[rowc]; lb = a.cell_start[rowc + xhi - nx + 1] - b0;
+                }
+            }
+        }
+        const int mine = la + lb;
+        int pe = mine;  // inclusive scan over the lanes: every lane's stretch of the scratch list
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, pe, o);
+            if (lane >= o) pe += t;
+        }
+        const int n_cand = __shfl_sync(kFull, pe, 31);
+        int32_t* tmp = smem_rows + kWarpsPerBlock * a.cap + wib * a.tmp_cap;
+        if (n_cand <= a.tmp_cap) {
+            // every lane writes out the slots of its row (a dozen shared-memory stores), then all 32 lanes walk the
+            // flattened list: one LDS per candidate instead of a shuffle search, two 32-wide steps of loads in flight
+            int32_t* mt = tmp + (pe - mine);
+            for (int k = 0; k < mine; ++k) mt[k] = k < la ? a0 + k : b0 + (k - la);
+            __syncwarp();
+#ifndef PANTEA_ROWS_RU
+#define PANTEA_ROWS_RU 2
+#endif
+            constexpr int RU = PANTEA_ROWS_RU;
+            for (int v0 = 0; v0 < n_cand; v0 += 32 * RU) {
+                int jj[RU];
+                Rec<float> rq[RU];
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    const int v = v0 + 32 * u + lane;
+                    jj[u] = v < n_cand ? tmp[v] : i;  // past the end: the atom itself (rejected)
+                    rq[u] = a.rec_screen[jj[u]];
+                }
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    const int j = jj[u];
+                    const Rec<float> rj = rq[u];
+                    float ax = fabsf(rif.x - rj.x), ay = fabsf(rif.y - rj.y), az = fabsf(rif.z - rj.z);
+                    ax = fminf(ax, flx - ax); ay = fminf(ay, fly - ay); az = fminf(az, flz - az);
+                    const float r2f = ax * ax + ay * ay + az * az;
+                    bool ok = r2f < lo_f && j != i;
+                    const bool ambiguous = (ok ? r2f <= a.screen_band : r2f <= hi_f) && j != i;
+                    if (ambiguous) {
+                        const Rec<T> rjx = rec[j];
+                        T dx = sub_rn(ri.x, rjx.x), dy = sub_rn(ri.y, rjx.y), dz = sub_rn(ri.z, rjx.z);
+                        dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz);
+                        const T rr = norm3_rn(dx, dy, dz);
+                        ok = (rr <= rc) && (rr > (T)0);
+                    }
+                    const unsigned m = __ballot_sync(kFull, ok);
+                    const int p = cnt + __popc(m & ((1u << lane) - 1u));
+                    if (ok && p < a.cap) L[p] = j | (rec_type(rj) << 28);
+                    cnt += __popc(m);
+                }
+            }
+        } else {
+            cnt = a.cap + 1;  // scratch too small for this many candidates: report as an overflow (the caller re-runs)
+        }
+    } else if (MODE == kModeCell && a.cell.r == 2) {
         // Half-width cells, 5 x 5 x 5 stencil: 125 (w/2)^3 = 15.6 w^3 of candidate volume instead of 27 w^3.  A (dy, dz)
         // row of the stencil now holds only ~17 candidates, so the 25 rows are not scanned one by one (half-empty
         // warps) but as ONE flattened candidate list: lane r < 25 owns row r -- up to two contiguous slot ranges, two
@@ -778,7 +873,15 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
         ra.screen_band = (float)(2.0 * (3.5 * rc * delta + 3.0 * delta * delta + 3.0e-7 * rc * rc));
     }
     const int blocks_w = (int)(((owned ? (int64_t)ra.n_owned : n) + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    const size_t smem = (size_t)kWarpsPerBlock * ws->cap * sizeof(int32_t);
+    // scratch of the row-per-lane scan: 125 half-width cells hold ~3.5 cap candidates on average
+    ra.tmp_cap = (use_cells && ca.r == 2 && ra.rec_screen) ? ((6 * ws->cap + 31) / 32 * 32) : 0;
+    const size_t smem = (size_t)kWarpsPerBlock * (ws->cap + ra.tmp_cap) * sizeof(int32_t);
+    {
+        static size_t configured[64] = {0};
+        int rc_s = use_cells ? opt_in_smem((const void*)neighbor_rows_kernel<T, kModeCell>, smem, configured, "neighbour rows: capacity too large for shared memory")
+                             : PANTEA_OK;
+        if (rc_s != PANTEA_OK) return rc_s;
+    }
     if (use_cells)
         neighbor_rows_kernel<T, kModeCell><<<blocks_w, kWarpsPerBlock * 32, smem, st>>>(rec, ra);
     else
