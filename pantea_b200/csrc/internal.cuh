@@ -196,7 +196,7 @@ struct pantea_workspace {
     int32_t* tmp_order = nullptr;  // [max_atoms]
     int32_t* cell_start = nullptr; // [cell_cap + 1]
     int32_t* cell_fill = nullptr;  // [cell_cap]
-    int32_t* scan_sums = nullptr;  // [cell_cap / 8192 + 1] tile sums of the two-launch cell scan
+    int32_t* scan_sums = nullptr;  // [2 * (cell_cap / 2048 + 2)] tile sums of the two-launch cell scan
     int32_t* cell_own = nullptr;   // [cell_cap + 1] exclusive scan of the owned atoms per cell (ranks that own a part)
     int32_t* cell_own_cnt = nullptr;  // [cell_cap + 1] owned atoms per cell (counted while binning, zeroed by the scan)
     int32_t* owned_slots = nullptr; // [max_atoms] cell-ordered slots of the owned atoms, ascending

@@ -71,10 +71,10 @@ __global__ void cell_assign_kernel(const T* __restrict__ pos, int n, CellArg ca,
 }
 
 // Exclusive scan of counts[0..n) into start[0..n] (start[n] = total); also zeroes `fill`.  Two launches: every block
-// of 1024 threads sums its tile of 8192 cells, then every block scans its own tile behind the sum of the tiles before
+// of 256 threads sums its tile of 2048 cells, then every block scans its own tile behind the sum of the tiles before
 // it (a single block took 38 us for the 3 x 10^4 half-width cells of the 10^5-atom box).  counts may alias start or
 // fill: a thread reads all of its inputs before it writes its outputs, and the tile sums are complete before any write.
-constexpr int kScanThreads = 1024, kScanK = 8, kScanTile = kScanThreads * kScanK;
+constexpr int kScanThreads = 256, kScanK = 8, kScanTile = kScanThreads * kScanK;
 
 __global__ void __launch_bounds__(kScanThreads) cell_tile_sums_kernel(const int32_t* __restrict__ counts, int n,
                                                                       int32_t* __restrict__ tile_sums,
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kScanThreads) cell_tile_sums_kernel(const int3
     if (lane == 0) warp_sums[wid] = x;
     __syncthreads();
     if (wid == 0) {
-        int w = warp_sums[lane];
+        int w = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(kFull, w, o);
         if (lane == 0) tile_sums[blockIdx.x] = w;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kScanThreads) cell_scan_kernel(const int32_t* 
     if (lane == 31) warp_sums[wid] = x;
     __syncthreads();
     if (wid == 0) {
-        int w = warp_sums[lane];
+        int w = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int y = __shfl_up_sync(kFull, w, o);

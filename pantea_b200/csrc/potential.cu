@@ -321,7 +321,7 @@ int ensure_cell_capacity(pantea_workspace* ws, int64_t ncells) {
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_start, 4 * (ncells + 1)));
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_fill, 4 * (ncells + 1)));
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_own, 4 * (ncells + 1)));
-    PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->scan_sums, 4 * 2 * (ncells / 8192 + 2)));
+    PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->scan_sums, 4 * 2 * (ncells / 2048 + 2)));
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_own_cnt, 4 * (ncells + 1)));
     PANTEA_CUDA_TRY(cudaMemset(ws->cell_own_cnt, 0, 4 * (ncells + 1)));
     ws->cell_cap = ncells;
