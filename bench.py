@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="diagnostics only: skip the oracle comparison before timing")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the secondary workloads (configs[1] preprocessing batch, configs[4] 10^6-atom box, FP32 mode)")
     ap.add_argument("--engine", default="brick", choices=["brick", "replicated"],
                     help="brick (default): spatial bricks, ghost positions pushed into the peers' mailboxes over NVLink by "
                          "the integration kernel, CUDA-graph steps (csrc/mgpu.cu); replicated: round-1 scheme, all "
@@ -162,7 +164,8 @@ def parity_check(md, lib, _lib, pos_h, types_h, box_h, dtype, rank, world, dev):
         specs = load_potential(GOLDEN / "h2o.json")
         t0 = time.perf_counter()
         _, _, f_o = c_oracle.energy_forces(specs, pos_h, types_h, box_h)
-        row_ptr, _ = c_oracle.neighbors(pos_h, types_h, box_h, 12.0)
+        # (the oracle's neighbour export is serial: counts are compared up to 3 x 10^5 atoms, forces always)
+        row_ptr = c_oracle.neighbors(pos_h, types_h, box_h, 12.0)[0] if n <= 300000 else None
         cpu_s = time.perf_counter() - t0
         f_o = torch.as_tensor(f_o, device=dev)
         rtol = 1e-10 if dtype == torch.float64 else 1e-5
@@ -170,12 +173,12 @@ def parity_check(md, lib, _lib, pos_h, types_h, box_h, dtype, rank, world, dev):
         err = (frc - f_o).abs()
         over = float((err / (rtol * (f_o.abs() + rms))).max())
         rel = float((err / f_o.abs().clamp_min(1e-300)).max())
-        n_equal = bool((counts.cpu().numpy() == np.diff(row_ptr).astype(np.int32)).all())
+        n_equal = bool((counts.cpu().numpy() == np.diff(row_ptr).astype(np.int32)).all()) if row_ptr is not None else None
         out = {"n_atoms": n, "max_err_over_tol": over, "rtol": rtol, "criterion": "|dF| <= rtol*(|F|+rms(F)) per component",
                "max_rel_F": rel, "max_abs_dF": float(err.max()), "rms_F": rms, "neighbors_equal": n_equal,
                "one_owner_per_atom": one_owner,
                "oracle": f"all {n} atoms, oracle/hdnnp_oracle.c, {threads} threads, {cpu_s:.1f} s",
-               "ok": bool(over <= 1.0 and n_equal and one_owner)}
+               "ok": bool(over <= 1.0 and n_equal is not False and one_owner)}
     flag = torch.tensor([0.0 if (out is None or out["ok"]) else 1.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MAX)
@@ -183,6 +186,157 @@ def parity_check(md, lib, _lib, pos_h, types_h, box_h, dtype, rank, world, dev):
         if rank == 0:
             print(json.dumps({"parity": out}), file=sys.stderr)
         raise SystemExit("bench.py: GPU forces / neighbour counts differ from the oracle; no throughput number is reported")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- secondary workloads
+def run_preprocess(pot, rank, world, dev, n_structs=10000, atoms=192, batch=1250):
+    """BASELINE.json configs[1]: ACSF values + gradients of 10 000 synthetic 192-atom water structures, structure s on
+    rank s mod world (reference acsf.py:47-120), then the scaler statistics of every element over the whole set
+    (trainer.py:68-88, scaler.py:249-283): per-batch two-pass statistics kernel, merged across batches and ranks.
+    Parity: eight random structures against the C oracle (values and gradients, 1e-10), statistics against torch."""
+    import torch
+
+    from pantea_b200 import engine
+    from pantea_b200.descriptors.scaler import DescriptorScaler
+    from pantea_b200.distributed import all_reduce_max, merge_scaler_params
+    from pantea_b200.utils.synthetic import water_box
+
+    mine = list(range(rank, n_structs, world))
+    ws = engine.Workspace(pot, batch * atoms, atoms - 1, torch.float64)
+    batches = []
+    for b0 in range(0, len(mine), batch):
+        ids = mine[b0:b0 + batch]
+        structs = [water_box(atoms, seed=2024 + s) for s in ids]
+        pos = torch.as_tensor(np.concatenate([x[0] for x in structs]), device=dev)
+        types = torch.as_tensor(np.concatenate([x[1] for x in structs]), dtype=torch.int32, device=dev)
+        boxes = torch.as_tensor(np.stack([x[2] for x in structs]), device=dev)
+        ptr = torch.arange(len(ids) + 1, dtype=torch.int32, device=dev) * atoms
+        idx = {el: torch.nonzero(types == pot.type_of[el]).flatten().to(torch.int32) for el in ("H", "O")}
+        batches.append((ids, structs, pos, types, boxes, ptr, idx))
+
+    def process(keep=False):
+        params = {"H": None, "O": None}
+        kept = []
+        for ids, structs, pos, types, boxes, ptr, idx in batches:
+            ws.bind_batch(pos, types, ptr, boxes, pot.r_cutoff, check=False)
+            res = {}
+            for el in ("H", "O"):
+                G, dG = ws.acsf(pot.slot(el), pot.n_symfunc[el], idx[el], True, True)
+                params[el] = DescriptorScaler.fit(G) if params[el] is None else DescriptorScaler.partial_fit(params[el], G)
+                res[el] = (G, dG)
+            if keep:
+                kept.append(res)
+        return params, kept
+
+    process()  # warm-up: capacities, lazy allocations
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    params, kept = process(keep=True)
+    merged = {el: merge_scaler_params(params[el]) for el in ("H", "O")}
+    b.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    all_reduce_max(ms)
+    ok, checked = True, 0
+    if rank == 0:
+        from oracle import c_oracle
+        from oracle.spec import load_potential
+        specs = load_potential(GOLDEN / "h2o.json")
+        rng = np.random.default_rng(11)
+        for _ in range(8):
+            bi = int(rng.integers(len(batches)))
+            si = int(rng.integers(len(batches[bi][0])))
+            p0, t0, b0 = batches[bi][1][si]
+            for spec, el in zip(specs, ("H", "O")):
+                centres = np.nonzero(t0 == spec.atom_type)[0]
+                G_o, dG_o = c_oracle.acsf(spec, p0, t0, b0, centres)
+                k = len(centres)
+                G, dG = kept[bi][el]
+                sl = slice(si * k, (si + 1) * k)
+                ok &= bool(np.abs(G[sl].cpu().numpy() - G_o).max() < 1e-10 * np.abs(G_o).max())
+                ok &= bool(np.abs(dG[sl].cpu().numpy() - dG_o).max() < 1e-10 * np.abs(dG_o).max())
+            checked += 1
+        if world == 1:  # the merged statistics against torch reductions over all descriptor rows
+            for el in ("H", "O"):
+                allG = torch.cat([r[el][0] for r in kept])
+                ok &= bool(torch.allclose(merged[el].mean, allG.mean(0), rtol=1e-10, atol=1e-14))
+                ok &= bool(torch.allclose(merged[el].sigma, allG.std(0, unbiased=False), rtol=1e-8, atol=1e-14))
+                ok &= bool(torch.equal(merged[el].minval, allG.min(0).values) and torch.equal(merged[el].maxval, allG.max(0).values))
+    t_s = float(ms.item()) * 1e-3
+    return {"workload": f"{n_structs} x {atoms}-atom water structures, ACSF values + gradients + scaler statistics "
+                        "[BASELINE.json configs[1]]", "value": n_structs / t_s, "unit": "structures/s",
+            "atoms_per_s": n_structs * atoms / t_s, "ms_total": float(ms.item()), "split": f"structure s on rank s mod {world}",
+            "scaler_samples": {el: int(merged[el].nsamples) for el in ("H", "O")},
+            "parity": {"structures_checked": checked, "ok": ok} if rank == 0 else None}
+
+
+def run_million(pot, rank, world, dev, dtype, steps=20):
+    """BASELINE.json configs[4]: 10^6-atom water box on `world` GPUs (strong scaling) and 125 000 atoms per GPU (weak
+    scaling), brick engine; forces of the initial state checked against the oracle on a sample of 20 000 atoms."""
+    import torch
+
+    from pantea_b200.brick import BrickMD
+    from pantea_b200.distributed import all_reduce_max
+    from pantea_b200.utils.synthetic import md_velocities, water_box
+
+    out = {}
+    for name, n_atoms in (("strong_1e6", 999999), ("weak_125k_per_gpu", 3 * (125000 * world // 3))):
+        pos_h, types_h, box_h = water_box(n_atoms)
+        vel_h = md_velocities(types_h)
+        t = lambda a, dt=dtype: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)  # noqa: E731
+        p0, v0 = t(pos_h), t(vel_h)
+        md = BrickMD(pot, p0, v0, t(types_h, torch.int32), [float(b) for b in box_h], DT, rank, world)
+        _, _, frc, owners = md.gather()
+        parity = None
+        if rank == 0:
+            from oracle import c_oracle
+            from oracle.spec import load_potential
+            specs = load_potential(GOLDEN / "h2o.json")
+            pin_oracle_threads(c_oracle)
+            m = min(n_atoms, 20000)
+            _, _, f_o = c_oracle.energy_forces(specs, pos_h, types_h, box_h, begin=0, end=m)
+            f_o = torch.as_tensor(f_o[:m], device=dev)
+            rtol = 1e-10 if dtype == torch.float64 else 1e-5
+            rms = float(f_o.pow(2).mean().sqrt())
+            over = float(((frc[:m].double() - f_o).abs() / (rtol * (f_o.abs() + rms))).max())
+            parity = {"atoms_checked": m, "max_err_over_tol": over, "rtol": rtol,
+                      "one_owner_per_atom": bool((owners == 1).all()), "ok": bool(over <= 1.0 and (owners == 1).all())}
+        for attempt in range(4):  # settle the capacities on one 25-step segment
+            md.run(SEGMENT)
+            try:
+                md.check_capacity()
+                ok = 0.0
+            except Exception:
+                ok = 1.0
+            flag = torch.tensor([ok], dtype=torch.float64, device=dev)
+            all_reduce_max(flag)
+            md.reset(p0, v0)
+            if float(flag.item()) == 0.0:
+                break
+        md.run(3)
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        md.run(steps)
+        b.record()
+        torch.cuda.synchronize()
+        md.check_capacity()
+        ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        all_reduce_max(ms)
+        out[name] = {"atoms": n_atoms, "value": n_atoms * steps / (float(ms.item()) * 1e-3), "unit": UNIT,
+                     "ms_per_step": float(ms.item()) / steps, "steps": steps, "bricks": list(md.grid.dims),
+                     "l2": "inputs larger than L2 (pair lists > 1 GB per step), no flush", "parity": parity}
+        md.close()
+        del md
+        torch.cuda.empty_cache()
     return out
 
 
@@ -582,6 +736,7 @@ def run_b200(args) -> None:
                "sample": f"one force+energy evaluation of {m} of the {n} atoms ({el:.1f} s); oracle/hdnnp_oracle.c, "
                          "OpenMP, cell-list gather; the reference's JAX path cannot run here (no jax)"}
 
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -600,7 +755,40 @@ def run_b200(args) -> None:
             "wall_s_timed_region": wall,
         }
         line.update(extra)
-        print(json.dumps(line))
+    # ---- secondary workloads (all ranks take part).  The headline line above is complete before they start; a watchdog
+    #      prints it without them if they fail to finish (a rank that died inside a collective must not cost the line)
+    import threading
+
+    def emit(extras_done, note=None):
+        if rank == 0:
+            line["preprocess"], line["million"] = extras_done.get("preprocess"), extras_done.get("million")
+            if note:
+                line["extras_note"] = note
+            print(json.dumps(line), flush=True)
+
+    extras = {}
+    run_extras = not args.no_extra and os.environ.get("PANTEA_BENCH_EXTRA", "1") != "0" and args.atoms <= 200000
+    if run_extras:
+        def bail():
+            emit(extras, "secondary workloads did not finish within the time limit")
+            os._exit(0)
+        watchdog = threading.Timer(float(os.environ.get("PANTEA_BENCH_EXTRA_LIMIT_S", "240")), bail)
+        watchdog.daemon = True
+        watchdog.start()
+        del md
+        if brick:
+            brick_md.close()
+        torch.cuda.empty_cache()
+        for name, fn in (("preprocess", lambda: run_preprocess(pot, rank, world, dev)),
+                         ("million", lambda: run_million(pot, rank, world, dev, dtype))):
+            try:
+                extras[name] = fn()
+            except Exception as exc:  # noqa: BLE001
+                extras[name] = {"error": f"{type(exc).__name__}: {exc}"}
+                if world > 1:
+                    break  # the ranks may be out of step: no further collectives
+        watchdog.cancel()
+    emit(extras)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -32,6 +32,24 @@ namespace pantea {
 // ORDER: also require j < k (the chunk's own neighbours in a same-type group); CLS: test j's cutoff-class bit (only
 // groups whose cutoff is shorter than the list radius); WRAP: minimum image on r_jk.  Two neighbours per iteration;
 // the staging array has one spare entry so that the odd tail can be read unconditionally.
+// true when the neighbours at row positions n1 and n2 of the centre in `slot` sit at exactly the same position as seen
+// from the centre (d_ij == d_ik in every component: the reference's r_jk is then 0 and it drops the triplet,
+// acsf.py:316-325).  Only called when the binning flagged coincident atoms and the staged single-precision vectors agree.
+template <typename T>
+__device__ __noinline__ bool coincident_neighbours(const Rec<T>* __restrict__ rec, const int32_t* __restrict__ row, int slot,
+                                                   int n1, int n2, T lx, T ly, T lz, bool pbc) {
+    const Rec<T> ri = rec[slot];
+    const Rec<T> r1 = rec[row[n1]], r2 = rec[row[n2]];
+    T d1[3] = {sub_rn(ri.x, r1.x), sub_rn(ri.y, r1.y), sub_rn(ri.z, r1.z)};
+    T d2[3] = {sub_rn(ri.x, r2.x), sub_rn(ri.y, r2.y), sub_rn(ri.z, r2.z)};
+    if (pbc) {
+        d1[0] = min_image(d1[0], lx); d1[1] = min_image(d1[1], ly); d1[2] = min_image(d1[2], lz);
+        d2[0] = min_image(d2[0], lx); d2[1] = min_image(d2[1], ly); d2[2] = min_image(d2[2], lz);
+    }
+    return d1[0] == d2[0] && d1[1] == d2[1] && d1[2] == d2[2];
+}
+
+template <typename T>
 struct FilterSweep {
     int32_t* list;
     int pair_cap, cls_bit, k_hi, kk;
@@ -39,6 +57,12 @@ struct FilterSweep {
     float rc2f, flx, fly, flz;
     float4 fk;
     bool k_ok;
+    // exact coincidence test, only when the binning saw atoms at the same position
+    bool exact, pbc;
+    const Rec<T>* rec;
+    const int32_t* row;
+    int slot, k_pos;
+    T lx, ly, lz;
     template <bool ORDER, bool CLS, bool WRAP>
     __device__ __forceinline__ int run(const float4* __restrict__ sf4, int js, int j_lo, int j_hi, int off) const {
         for (int aj = j_lo; aj < j_hi; aj += 2) {
@@ -50,6 +74,8 @@ struct FilterSweep {
                 if (WRAP) { ex = min_image(ex, flx); ey = min_image(ey, fly); ez = min_image(ez, flz); }
                 const float d2 = ex * ex + ey * ey + ez * ez;
                 live[c] = k_ok && d2 < rc2f;
+                if (exact && live[c] && fj[c].x == fk.x && fj[c].y == fk.y && fj[c].z == fk.z && js + aj + c != k_pos)
+                    live[c] = !coincident_neighbours<T>(rec, row, slot, js + aj + c, k_pos, lx, ly, lz, pbc);
                 if (CLS) live[c] = live[c] && (__float_as_int(fj[c].w) & cls_bit);
                 if (ORDER) live[c] = live[c] && aj + c < kk;
             }
@@ -131,7 +157,9 @@ __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const At
         // Same-type groups take the unordered pairs j < k: neighbours before the chunk pair with all of its lanes, the
         // chunk's own neighbours need the order test.  Mixed groups sweep the bucket that leaves fewer idle lanes.
         // The pair order (k chunk, j, k) is fixed, hence the evaluation's summation order is deterministic.
-        FilterSweep sw;
+        FilterSweep<T> sw;
+        sw.exact = a.dup_always || (a.dup_flag && *a.dup_flag != 0); sw.pbc = pbc; sw.rec = a.rec; sw.row = a.nbr + (size_t)slot * a.cap;
+        sw.slot = slot; sw.lx = lx; sw.ly = ly; sw.lz = lz;
         sw.list = list; sw.pair_cap = pair_cap; sw.lt_mask = lt_mask; sw.rc2f = rc2f; sw.cls_bit = 1 << grp.cls;
         sw.flx = flx; sw.fly = fly; sw.flz = flz;
         const bool swap = !same && nj * ((nk + 31) >> 5) > nk * ((nj + 31) >> 5);
@@ -143,6 +171,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32) pair_filter_kernel(const At
             sw.fk = sf4[ks + (kk < nks ? kk : 0)];
             sw.k_ok = kk < nks && (__float_as_int(sw.fk.w) & sw.cls_bit);
             sw.k_hi = (ks + kk) << 16;
+            sw.k_pos = ks + (kk < nks ? kk : 0);
             sw.kk = kk;
             const int j_full = same ? min(njs, k0) : njs, j_diag = same ? min(njs, k0 + 31) : njs;
             switch (variant) {
@@ -906,6 +935,8 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
     a.wrap_jk = ws->boxes ? 1 : (ws->has_box && 0.5 * lmin < 2.0 * ws->rc * (1.0 + 1e-9) ? 1 : 0);
     a.rc_list = ws->rc;
     a.skin = ws->skin_active ? (float)ws->skin : 0.f;
+    a.dup_flag = ws->mode == kModeCell ? ws->wide_flag + 1 : nullptr;
+    a.dup_always = ws->mode == kModeCell ? 0 : 1;
     a.screen_t = a.skin > 0.f ? 0.f : (float)g_gauss_screen.load(std::memory_order_relaxed);  // (kept lists must not depend on the positions)
     a.filter_guard = nullptr;
     a.tables = pot->dev; a.n_types = pot->n_elements; a.element_slot = element_slot;

@@ -111,6 +111,12 @@ struct Filter2 {
     int32_t* strip;      // the warp's shared-memory emission strip
     int pair_cap, off, fill, lane;
     float rc2f;
+    // exact coincidence test (only when the binning saw atoms at the same position): staged index -> exact difference
+    const void* rec;     // Rec<T>[]
+    const int32_t* row;  // the centre's neighbour row
+    int slot;
+    double blx, bly, blz;
+    bool pbc, exact;
     float r2max;  // Gaussian screening: pairs with r_j^2 + r_k^2 + r_jk^2 above it are dropped (huge: no screening)
     bool cls_test, screen;
 
@@ -173,6 +179,24 @@ struct Filter2 {
     // selected by res_shift) against the swept range [s_begin, s_begin + ns): tiles of 32 broadcast reads
     // tri: resident chunk and swept range are the same neighbours -- only the pairs with the swept index below the
     // resident one are kept (lower triangle of the tile)
+    // true when staged neighbours n1 and n2 sit at exactly the same position as seen from the centre (d_ij == d_ik in
+    // every component: the reference's r_jk is then 0 and it drops the triplet, acsf.py:316-325)
+    template <typename T>
+    __device__ __noinline__ bool coincident(int n1, int n2) const {
+        const Rec<T>* rc_ = (const Rec<T>*)rec;
+        const T lx = (T)blx, ly = (T)bly, lz = (T)blz;
+        const Rec<T> ri = rc_[slot];
+        const Rec<T> r1 = rc_[row[n1]], r2 = rc_[row[n2]];
+        T d1[3] = {sub_rn(ri.x, r1.x), sub_rn(ri.y, r1.y), sub_rn(ri.z, r1.z)};
+        T d2[3] = {sub_rn(ri.x, r2.x), sub_rn(ri.y, r2.y), sub_rn(ri.z, r2.z)};
+        if (pbc) {
+            d1[0] = min_image(d1[0], lx); d1[1] = min_image(d1[1], ly); d1[2] = min_image(d1[2], lz);
+            d2[0] = min_image(d2[0], lx); d2[1] = min_image(d2[1], ly); d2[2] = min_image(d2[2], lz);
+        }
+        return d1[0] == d2[0] && d1[1] == d2[1] && d1[2] == d2[2];
+    }
+
+    template <typename T>
     __device__ __forceinline__ void rect(int r0, int nres, int res_shift, int s_begin, int ns, bool tri = false) {
         const float4 fl = sf4[r0 + (lane < nres ? lane : 0)];
         const bool l_ok = lane < nres && (!cls_test || fl.w < rc2f);
@@ -199,6 +223,15 @@ struct Filter2 {
             if (cls_test) mask &= __ballot_sync(kFullMask, lane < nb && sf4[s_begin + s0 + lane].w < rc2f);
             if (!l_ok) mask = 0;
             if (tri) mask &= (1u << lane) - 1u;
+            if (exact) {  // rare: drop the pairs of exactly coincident neighbours (candidates: identical staged vectors)
+                unsigned zz = mask;
+                while (zz) {
+                    const int b = __ffs(zz) - 1;
+                    zz &= zz - 1;
+                    const float4 fs = sf4[s_begin + s0 + b];
+                    if (fs.x == fl.x && fs.y == fl.y && fs.z == fl.z && coincident<T>(r0 + lane, s_begin + s0 + b)) mask &= ~(1u << b);
+                }
+            }
             emit<false>(mask, nb, res_part + (((s_begin + s0) * kRec2Bytes) << (16 - res_shift)), stride, 0, 0);
         }
     }
@@ -295,6 +328,8 @@ __global__ void __launch_bounds__(kFilter2Warps * 32, PANTEA_FILTER2_MINBLOCKS) 
     Filter2 f;
     f.sf4 = sf4; f.list = a.pairs + (size_t)w * a.pair_cap; f.strip = strip; f.pair_cap = a.pair_cap; f.off = 0; f.fill = 0;
     f.lane = lane; f.rc2f = rc2f;
+    f.rec = a.rec; f.row = a.nbr + (size_t)slot * a.cap; f.slot = slot; f.blx = (double)lx; f.bly = (double)ly; f.blz = (double)lz;
+    f.pbc = pbc; f.exact = a.dup_flag && *a.dup_flag != 0;
     f.cls_test = tab.n_cls > 0 && tab.cls[0].rc + (double)a.skin < a.rc_list;  // rows reach beyond the cutoff
     const int pad_entry = (sg.total * kRec2Bytes) | ((sg.total * kRec2Bytes) << 16);
     int n_real = 0;
@@ -363,11 +398,11 @@ __global__ void __launch_bounds__(kFilter2Warps * 32, PANTEA_FILTER2_MINBLOCKS) 
                 const int q = it - full;
                 r0 = sb + 32 * q; nres = min(32, ns - 32 * q); shift = 16 - rshift; s_begin = rb + 32 * full; s_len = rem;
             }
-            if (s_len > 0) f.rect(r0, nres, shift, s_begin, s_len);
+            if (s_len > 0) f.template rect<T>(r0, nres, shift, s_begin, s_len);
 #ifdef PANTEA_FILTER2_WRAP_DIAG
             if (do_diag) f.diag(r0, nres);
 #else
-            if (do_diag && nres > 1) f.rect(r0, nres, 16, r0, nres, true);  // the chunk's own triangle: a masked tile
+            if (do_diag && nres > 1) f.template rect<T>(r0, nres, 16, r0, nres, true);  // the chunk's own triangle: a masked tile
 #endif
         }
         n_real -= f.finish_group(pad_entry);

@@ -87,6 +87,7 @@ template <> __device__ __forceinline__ double t_fmod2<double>(double a, double b
 template <> __device__ __forceinline__ float t_fmod2<float>(float a, float b) { return fmodf(a, b); }
 template <typename T>
 __device__ __forceinline__ T wrap1(T x, T box) {  // floored remainder, as md.cu / box.py:123-126
+    if (x >= (T)0 && x < box) return x;  // already inside: the remainder is x itself (fmod is the slow path)
     T m = t_fmod2<T>(x, box);
     if (m != (T)0 && ((m < (T)0) != (box < (T)0))) m = add_rn(m, box);
     return m;
@@ -111,6 +112,14 @@ __global__ void mgpu_integrate_push_kernel(int n, const uint8_t* __restrict__ ro
     const PeerTable& pt = *pt_p;
     const unsigned long long next = *epoch_p + 1;
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    // brick bounds of every rank, once per block
+    __shared__ double s_lo[kMaxRanks][3], s_hi[kMaxRanks][3];
+    if (threadIdx.x < bt.world) {
+        const int r = threadIdx.x, pz = bt.dims[2], py = bt.dims[1];
+        const int c[3] = {r / (py * pz), (r / pz) % py, r % pz};
+        for (int d = 0; d < 3; ++d) { s_lo[r][d] = bt.edges[d][c[d]]; s_hi[r][d] = bt.edges[d][c[d] + 1]; }
+    }
+    __syncthreads();
     if (id < n && role[id] == 2) {
         const T* vel = (const T*)pt.vel[bt.rank];
         const T* frc = (const T*)pt.frc[bt.rank];
@@ -126,7 +135,11 @@ __global__ void mgpu_integrate_push_kernel(int n, const uint8_t* __restrict__ ro
         m.x = x[0]; m.y = x[1]; m.z = x[2]; m.stamp = (decltype(m.stamp))next;
         const int owner = brick_owner(bt, (double)x[0], (double)x[1], (double)x[2]);
         for (int r = 0; r < bt.world; ++r) {
-            if (!in_shell(bt, r, (double)x[0], (double)x[1], (double)x[2])) continue;
+            bool inside = true;
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                if (bt.dims[d] > 1 && axis_gap((double)x[d], s_lo[r][d], s_hi[r][d], bt.box[d]) > bt.reach) inside = false;
+            if (!inside) continue;
             ((MailRec<T>*)pt.mail[r])[(size_t)(next & 1) * n + id] = m;  // NVLink store when r is a peer
             if (r == owner && r != bt.rank) {  // the atom changes its owner: velocity and force rows travel with it
                 T* pv = (T*)pt.vel[r];

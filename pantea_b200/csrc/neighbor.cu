@@ -51,6 +51,7 @@ __global__ void cell_assign_kernel(const T* __restrict__ pos, int n, CellArg ca,
                                    int32_t* __restrict__ own_count, int own_begin, int own_end) {
     if (guard && *guard == 0) return;  // Verlet skin: the rows of the last rebuild are still valid
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) wide_flag[1] = 0;  // "two atoms of one cell at the same wrapped position" (set by cell_sort_pack_kernel)
     if (i >= n) return;
     if (role && role[i] == 0) { cell_of[i] = -1; return; }  // not on this rank (brick decomposition)
     {   // the screening pass measures true minimum-image distances; they equal the reference's single-shift ones only
@@ -187,7 +188,8 @@ __global__ void cell_sort_pack_kernel(const T* __restrict__ pos, const int32_t* 
                                       int32_t* __restrict__ slot_of, Rec<float>* __restrict__ rec_screen, BoxArg box,
                                       int32_t* __restrict__ cell_fill, const int32_t* __restrict__ guard,
                                       int own_begin, int own_end, int32_t* __restrict__ cell_own,
-                                      int32_t* __restrict__ tcount, const uint8_t* __restrict__ role) {
+                                      int32_t* __restrict__ tcount, const uint8_t* __restrict__ role,
+                                      int32_t* __restrict__ dup_flag) {
     if (guard && *guard == 0) return;
     auto is_owned = [&](int idx) { return role ? role[idx] == 2 : (idx >= own_begin && idx < own_end); };
     int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -214,6 +216,16 @@ __global__ void cell_sort_pack_kernel(const T* __restrict__ pos, const int32_t* 
             f.z = (float)(z - box.lz * floor(z / box.lz));
             rec_set(f, bucket_of(types[mine], n_types), mine);
             rec_screen[lo + rank] = f;
+            // Coincident atoms (the reference drops a triplet whose two neighbours sit at the same position, acsf.py:325)
+            // share a cell and their wrapped single-precision coordinates: raise the flag that sends the pair filter
+            // through its exact test.  Conservative: equal floats / more than 32 atoms in a cell are enough.
+            if (hi - lo > 32) *dup_flag = 1;
+            const unsigned act = __activemask();
+            const int cnt = min(32, hi - (a - lane));
+            for (int b = 0; b < cnt; ++b) {
+                const float ox = __shfl_sync(act, f.x, b), oy = __shfl_sync(act, f.y, b), oz = __shfl_sync(act, f.z, b);
+                if (b != lane && ox == f.x && oy == f.y && oz == f.z) *dup_flag = 1;
+            }
         }
     }
 }
@@ -826,7 +838,7 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
         if (!guard || forced) {  // device-decided rebuilds find the scratch zeroed by the previous rebuild's kernels
             PANTEA_CUDA_TRY(cudaMemsetAsync(ws->cell_fill, 0, 4 * (ncells + 1), st));
             if (owned) PANTEA_CUDA_TRY(cudaMemsetAsync(ws->cell_own_cnt, 0, 4 * (ncells + 1), st));
-            PANTEA_CUDA_TRY(cudaMemsetAsync(ws->wide_flag, 0, 4, st));
+            PANTEA_CUDA_TRY(cudaMemsetAsync(ws->wide_flag, 0, 8, st));
         }
         cell_assign_kernel<T><<<blocks_n, threads, 0, st>>>(pos, (int)n, ca, ba, ws->cell_of, ws->cell_fill, ws->wide_flag, guard, role,
                                                             owned ? ws->cell_own_cnt : nullptr, own_lo, own_hi);
@@ -840,7 +852,7 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
         cell_sort_pack_kernel<T><<<blocks_c, threads, 0, st>>>(pos, types, ws->n_types, ws->cell_start, (int)ncells,
                                                                ws->tmp_order, rec, ws->slot_of,
                                                                (Rec<float>*)ws->rec_screen, ba, ws->cell_fill, guard,
-                                                               own_lo, own_hi, owned ? ws->cell_own : nullptr, ws->nbr_tcount, role);
+                                                               own_lo, own_hi, owned ? ws->cell_own : nullptr, ws->nbr_tcount, role, ws->wide_flag + 1);
         PANTEA_LAUNCH_CHECK();
         if (owned) {  // compact list of the owned atoms' slots (cell order) behind the scanned per-cell owned counts
             owned_fill_kernel<T><<<blocks_c, threads, 0, st>>>(rec, ws->cell_start, (int)ncells, ws->cell_own, own_lo, own_hi,

@@ -235,7 +235,7 @@ int pantea_workspace_create(const pantea_potential* pot, int64_t max_atoms, int3
     };
     alloc(&ws->rec, rsz * max_atoms);
     if (dtype == PANTEA_F64) alloc(&ws->rec_screen, sizeof(Rec<float>) * max_atoms);
-    alloc((void**)&ws->wide_flag, 4);
+    alloc((void**)&ws->wide_flag, 8);  // [0] atoms far outside the box, [1] coincident atoms present
     alloc(&ws->pos_ref, esz * 3 * max_atoms);
     alloc((void**)&ws->skin_flags, 4 * 4);
     alloc((void**)&ws->slot_of, 4 * max_atoms);

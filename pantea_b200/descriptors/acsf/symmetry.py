@@ -9,6 +9,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import NamedTuple, Optional
 
+import torch
+
 from pantea_b200.descriptors.acsf.cutoff import CutoffFunction
 from pantea_b200.types import Element
 
@@ -40,6 +42,10 @@ class G1(RadialSymmetryFunction):
     cfn: CutoffFunction
     kind = 1
 
+    def __call__(self, rij):
+        """Reference `radial.py:39-41`."""
+        return self.cfn(rij)
+
 
 @dataclass(frozen=True)
 class G2(RadialSymmetryFunction):
@@ -47,6 +53,11 @@ class G2(RadialSymmetryFunction):
     r_shift: float
     eta: float
     kind = 2
+
+    def __call__(self, rij):
+        """Reference `radial.py:59-61`."""
+        rij = torch.as_tensor(rij)
+        return torch.exp(-self.eta * (rij - self.r_shift) ** 2) * self.cfn(rij)
 
 
 @dataclass(frozen=True)
@@ -58,6 +69,12 @@ class G3(AngularSymmetryFunction):
     r_shift: float
     kind = 3
 
+    def __call__(self, rij, rik, rjk, cost):
+        """Reference `angular.py:51-66` (`r_shift` is ignored there too)."""
+        rij, rik, rjk, cost = (torch.as_tensor(t) for t in (rij, rik, rjk, cost))
+        return (2.0 ** (1.0 - self.zeta) * torch.pow(1 + self.lambda0 * cost, self.zeta)
+                * torch.exp(-self.eta * (rij**2 + rik**2 + rjk**2)) * self.cfn(rij) * self.cfn(rik) * self.cfn(rjk))
+
 
 @dataclass(frozen=True)
 class G9(AngularSymmetryFunction):
@@ -67,3 +84,9 @@ class G9(AngularSymmetryFunction):
     lambda0: float
     r_shift: float
     kind = 9
+
+    def __call__(self, rij, rik, rjk, cost):
+        """Reference `angular.py:92-107`: no r_jk terms, `r_shift` ignored."""
+        rij, rik, cost = (torch.as_tensor(t) for t in (rij, rik, cost))
+        return (2.0 ** (1.0 - self.zeta) * torch.pow(1 + self.lambda0 * cost, self.zeta)
+                * torch.exp(-self.eta * (rij**2 + rik**2)) * self.cfn(rij) * self.cfn(rik))

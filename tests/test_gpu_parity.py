@@ -542,3 +542,24 @@ def test_ragged_batch_of_structures(pot):
             G_o, dG_o = c_oracle.acsf(spec, p_s, t_s, b_s)
             _assert_descriptor_close(G[ptr[s]:ptr[s + 1]], dG[ptr[s]:ptr[s + 1]], G_o, dG_o, FP64_TOL)
 
+
+
+# ------------------------------------------------------------------------------------------ coincident neighbours
+@pytest.mark.parametrize("n_atoms", [24, 12000])
+def test_coincident_neighbours_are_excluded_exactly(n_atoms, pot):
+    """Two neighbours j != k of a centre at bit-identical positions have r_jk = 0 and the reference drops the triplet
+    (acsf.py:325).  A few atoms are moved onto the position of another atom of the same and of the other element (small
+    system: all-pairs kernels; large system: cell list, fast path with the binning's coincidence flag)."""
+    pos, types, box = water_box(n_atoms)
+    pos = pos.copy()
+    rng = np.random.default_rng(3)
+    idx = rng.choice(n_atoms, size=6, replace=False)
+    for a, b in zip(idx[:3], idx[3:]):
+        pos[a] = pos[b]
+    dev = device_potential_from_specs(pot)
+    ws = _workspace(dev, n_atoms)
+    ws.bind(cuda(pos), cuda(types, torch.int32), box, dev.r_cutoff)
+    _, e_atom, f = ws.energy_forces(False, True, True)
+    _, ea_o, f_o = c_oracle.energy_forces(pot, pos, types, box)
+    assert rel_err(e_atom.cpu().numpy(), ea_o) < 1e-10
+    assert rel_err(f.cpu().numpy(), f_o) < 1e-10
