@@ -516,6 +516,24 @@ def run_b200(args) -> None:
     if not capacity_ok():
         raise SystemExit("bench.py: a capacity flag was raised inside the timed region; the measurement is void")
     max_seen_main = max_seen
+    fp32_info = None
+    if brick and dtype == torch.float64 and not args.no_extra:
+        # secondary measurement: the same K steps in the mixed mode (symmetry functions in single precision on the same
+        # double-precision state; pantea_workspace_set_compute_precision) -- the north star's "FP32 mode"
+        md.ws.set_compute_precision(32)
+        md.reset(pos0, vel0)
+        par32 = None if args.no_parity else parity_check(md, lib, _lib, pos_h, types_h, box_h, torch.float32, rank, world, dev)
+        settle_capacities()
+        ms32, _, _ = timed_steps(args.steps)
+        if not capacity_ok():
+            raise SystemExit("bench.py: a capacity flag was raised inside the mixed-precision timed region")
+        fp32_info = {"value": n * args.steps / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32 / args.steps,
+                     "speedup_over_f64": ms_total / ms32,
+                     "what": "same K steps, symmetry functions and their gradients in FP32 (difference vectors formed in "
+                             "FP64, state / scaler / networks / integrator FP64); tolerance of the mode 1e-5",
+                     "parity": par32}
+        md.ws.set_compute_precision(64)
+        md.reset(pos0, vel0)
     engine_info = None
     if brick:
         own = torch.tensor([float(md.owned_count())], dtype=torch.float64, device=dev)
@@ -751,7 +769,7 @@ def run_b200(args) -> None:
                        "trajectory": f"timed steps replay {SEGMENT}-step segments from the initial state (untimed reset)"},
             "parity": parity,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "verlet_skin": skin_info, "halo_exchange": halo_info,
+            "fp32": fp32_info, "verlet_skin": skin_info, "halo_exchange": halo_info,
             "wall_s_timed_region": wall,
         }
         line.update(extra)

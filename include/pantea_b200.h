@@ -174,6 +174,13 @@ int pantea_energy_forces(pantea_workspace* ws, void* e_atom, void* forces, void*
    radial weights, r_jk from the unit-vector dot product).  Same results within ~1e-13 relative.  enable = 0 keeps every
    call on the generic kernels (diagnostics / parity tests); returns the previous setting.  Process-wide. */
 int pantea_set_fast_path(int32_t enable);
+/* Mixed precision of a PANTEA_F64 workspace (reference: `default_dtype.FLOATX = float32`, types.py:13-30, selects single
+   precision for everything; here the state stays double so that large boxes lose nothing): bits = 32 evaluates the
+   symmetry functions and their gradients in single precision -- the difference vectors r_i - r_j are still formed in
+   double -- on the specialised kernels (same eligibility as pantea_set_fast_path; otherwise the setting has no effect);
+   scaler, networks, forces and the integrator stay double.  Results agree with the double evaluation to ~1e-6
+   relative (tolerance of the mode: 1e-5).  bits = 64 (default) restores the double evaluation. */
+int pantea_workspace_set_compute_precision(pantea_workspace* ws, int32_t bits);
 /* Gaussian screening of the specialised kernels: within one angular group of one centre, a triplet whose Gaussian weight
    exp(-eta (r_ij^2 + r_ik^2 + r_jk^2)) is below exp(-threshold) times the weight of the pair formed by the centre's two
    nearest neighbours of the group's types is not evaluated (it is dropped when the pair lists are built).  Active only

@@ -83,6 +83,7 @@ PROTOTYPES = {
     "pantea_l2_flush": (C.c_int, [_VP, _I64, _VP]),
     "pantea_workspace_set_counters": (C.c_int, [_VP, _VP]),
     "pantea_eval_timing": (C.c_int, [_I32, C.POINTER(C.c_float)]),
+    "pantea_workspace_set_compute_precision": (C.c_int, [_VP, _I32]),
     "pantea_set_fast_path": (C.c_int, [_I32]),
     "pantea_set_gauss_screen": (_DBL, [_DBL]),
     "pantea_workspace_set_skin": (C.c_int, [_VP, _DBL]),

@@ -935,6 +935,7 @@ static int atom_kernel_typed(pantea_workspace* ws, int element_slot, const int32
     a.wrap_jk = ws->boxes ? 1 : (ws->has_box && 0.5 * lmin < 2.0 * ws->rc * (1.0 + 1e-9) ? 1 : 0);
     a.rc_list = ws->rc;
     a.skin = ws->skin_active ? (float)ws->skin : 0.f;
+    a.rec_bytes = ws->compute32 ? 48 : 80;
     a.dup_flag = ws->mode == kModeCell ? ws->wide_flag + 1 : nullptr;
     a.dup_always = ws->mode == kModeCell ? 0 : 1;
     a.screen_t = a.skin > 0.f ? 0.f : (float)g_gauss_screen.load(std::memory_order_relaxed);  // (kept lists must not depend on the positions)
@@ -1054,6 +1055,15 @@ int atom_kernel_launch(pantea_workspace* ws, int element_slot, const int32_t* ce
 using namespace pantea;
 
 extern "C" {
+
+int pantea_workspace_set_compute_precision(pantea_workspace* ws, int32_t bits) {
+    if (!ws) return fail(PANTEA_EINVAL, "pantea_workspace_set_compute_precision: NULL workspace");
+    if (bits != 32 && bits != 64) return fail(PANTEA_EINVAL, "pantea_workspace_set_compute_precision: bits must be 32 or 64");
+    if (bits == 32 && ws->dtype != PANTEA_F64) return fail(PANTEA_EINVAL, "pantea_workspace_set_compute_precision: the mixed mode belongs to PANTEA_F64 workspaces (a PANTEA_F32 workspace computes in single precision throughout)");
+    const bool want = bits == 32;
+    if (want != ws->compute32) { ws->compute32 = want; ws->lists_valid = false; ++ws->arg_epoch; }
+    return PANTEA_OK;
+}
 
 int pantea_set_fast_path(int32_t enable) {
     const int old = g_fast_path.exchange(enable ? 1 : 0);

@@ -102,6 +102,9 @@ __device__ __forceinline__ D2 lds128(const unsigned char* p) { return *reinterpr
 // ------------------------------------------------------------------------------------------------
 // pair filter
 // ------------------------------------------------------------------------------------------------
+#ifndef PANTEA_EXACT_ON
+#define PANTEA_EXACT_ON 1
+#endif
 constexpr int kStrip2 = 1024 + 128;  // entries of a warp's emission strip: one full tile behind an unflushed remainder
 
 // State of one warp's walk over the angular groups of its atom.
@@ -110,6 +113,7 @@ struct Filter2 {
     int32_t* list;       // the atom's pair list in global memory
     int32_t* strip;      // the warp's shared-memory emission strip
     int pair_cap, off, fill, lane;
+    int rb;  // bytes per staged neighbour record of the evaluation that will walk the list (80: double, 48: single)
     float rc2f;
     // exact coincidence test (only when the binning saw atoms at the same position): staged index -> exact difference
     const void* rec;     // Rec<T>[]
@@ -182,7 +186,7 @@ struct Filter2 {
     // true when staged neighbours n1 and n2 sit at exactly the same position as seen from the centre (d_ij == d_ik in
     // every component: the reference's r_jk is then 0 and it drops the triplet, acsf.py:316-325)
     template <typename T>
-    __device__ __noinline__ bool coincident(int n1, int n2) const {
+    __device__ __forceinline__ bool coincident(int n1, int n2) const {
         const Rec<T>* rc_ = (const Rec<T>*)rec;
         const T lx = (T)blx, ly = (T)bly, lz = (T)blz;
         const Rec<T> ri = rc_[slot];
@@ -200,8 +204,8 @@ struct Filter2 {
     __device__ __forceinline__ void rect(int r0, int nres, int res_shift, int s_begin, int ns, bool tri = false) {
         const float4 fl = sf4[r0 + (lane < nres ? lane : 0)];
         const bool l_ok = lane < nres && (!cls_test || fl.w < rc2f);
-        const int res_part = ((r0 + lane) * kRec2Bytes) << res_shift;
-        const int stride = kRec2Bytes << (16 - res_shift);
+        const int res_part = ((r0 + lane) * rb) << res_shift;
+        const int stride = rb << (16 - res_shift);
         const float al = r2max - fl.w;  // screening: r_jk^2 must stay below al - r_s^2
         for (int s0 = 0; s0 < ns; s0 += 32) {
             const int nb = min(32, ns - s0);
@@ -223,7 +227,7 @@ struct Filter2 {
             if (cls_test) mask &= __ballot_sync(kFullMask, lane < nb && sf4[s_begin + s0 + lane].w < rc2f);
             if (!l_ok) mask = 0;
             if (tri) mask &= (1u << lane) - 1u;
-            if (exact) {  // rare: drop the pairs of exactly coincident neighbours (candidates: identical staged vectors)
+            if (PANTEA_EXACT_ON && exact) {  // rare: drop the pairs of exactly coincident neighbours (candidates: identical staged vectors)
                 unsigned zz = mask;
                 while (zz) {
                     const int b = __ffs(zz) - 1;
@@ -232,7 +236,7 @@ struct Filter2 {
                     if (fs.x == fl.x && fs.y == fl.y && fs.z == fl.z && coincident<T>(r0 + lane, s_begin + s0 + b)) mask &= ~(1u << b);
                 }
             }
-            emit<false>(mask, nb, res_part + (((s_begin + s0) * kRec2Bytes) << (16 - res_shift)), stride, 0, 0);
+            emit<false>(mask, nb, res_part + (((s_begin + s0) * rb) << (16 - res_shift)), stride, 0, 0);
         }
     }
 
@@ -258,8 +262,8 @@ struct Filter2 {
         }
         if (!l_ok) mask = 0;
         // entry: lane's record in the low half, partner L + 1 + b (minus nres once it wraps) in the high half
-        const int e0 = ((r0 + lane) * kRec2Bytes) | (((r0 + lane + 1) * kRec2Bytes) << 16);
-        emit<true>(mask, h, e0, kRec2Bytes << 16, nres - 1 - lane, (nres * kRec2Bytes) << 16);
+        const int e0 = ((r0 + lane) * rb) | (((r0 + lane + 1) * rb) << 16);
+        emit<true>(mask, h, e0, rb << 16, nres - 1 - lane, (nres * rb) << 16);
     }
 };
 
@@ -331,7 +335,8 @@ __global__ void __launch_bounds__(kFilter2Warps * 32, PANTEA_FILTER2_MINBLOCKS) 
     f.rec = a.rec; f.row = a.nbr + (size_t)slot * a.cap; f.slot = slot; f.blx = (double)lx; f.bly = (double)ly; f.blz = (double)lz;
     f.pbc = pbc; f.exact = a.dup_flag && *a.dup_flag != 0;
     f.cls_test = tab.n_cls > 0 && tab.cls[0].rc + (double)a.skin < a.rc_list;  // rows reach beyond the cutoff
-    const int pad_entry = (sg.total * kRec2Bytes) | ((sg.total * kRec2Bytes) << 16);
+    f.rb = a.rec_bytes;
+    const int pad_entry = (sg.total * f.rb) | ((sg.total * f.rb) << 16);
     int n_real = 0;
     for (int gi = 0; gi < tab.n_groups; ++gi) {
         if (lane == 0) off_out[gi] = f.off < f.pair_cap ? f.off : f.pair_cap;
@@ -657,6 +662,235 @@ __global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2_MINBLOCKS) hdnnp
 }
 
 // ------------------------------------------------------------------------------------------------
+// evaluation in single precision (mixed mode of a double-precision workspace: pantea_workspace_set_compute_precision)
+// ------------------------------------------------------------------------------------------------
+// Positions, velocities and forces stay double; the difference vectors d_ij are formed in double (exact minimum image,
+// no loss at large box lengths) and only then rounded, and everything from there to the summed symmetry functions is
+// FP32: 48-byte records [d_x d_y d_z r^2 | 1/r W Q - | fc q - -] (12-bank stride: conflict-free LDS.128), r_jk from the
+// difference of the two vectors (the dot-product form cancels too much in FP32), MUFU reciprocal root / exp2 /
+// reciprocal.  The sums leave the kernel as doubles; scaler and network stay double (mlp_force_kernel).  Tolerance of
+// the mode: 1e-5 relative (north star).
+constexpr int kRec2fBytes = 48;
+#ifndef PANTEA_EVAL2F_MINBLOCKS
+#define PANTEA_EVAL2F_MINBLOCKS 6
+#endif
+
+__host__ __device__ inline size_t eval2f_smem_bytes(int scap, int n_sf) {
+    return ((size_t)(scap + 1) * kRec2fBytes + (size_t)n_sf * 4 * 8 + 15) & ~size_t(15);
+}
+
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqf(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float4 lds128f(const unsigned char* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int ZM1>
+__device__ __forceinline__ void angular2f(const unsigned char* __restrict__ snb, const int32_t* __restrict__ list, int n_iter,
+                                          float neta_l2e, float lam, float zl, int zm1_rt, float rc, int lane, int* stage,
+                                          double& oG, double& oX, double& oY, double& oZ) {
+    constexpr int NU = kNU2;
+    constexpr float kL2E = 1.4426950408889634f;
+    const float m2l_inv_rc = -2.0f * kL2E / rc, two_l2e = 2.0f * kL2E;
+    float aG[NU], aX[NU], aY[NU], aZ[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) { aG[u] = 0; aX[u] = 0; aY[u] = 0; aZ[u] = 0; }
+    constexpr int CH = kChunk2;
+    const int n_chunks = (n_iter + CH - 1) / CH;
+    auto stage_chunk = [&](int chunk) {
+        int* dst = stage + (chunk & 1) * (CH * 32);
+        const int32_t* src = list + (size_t)chunk * (CH * 32);
+#pragma unroll
+        for (int q = 0; q < CH / 4; ++q) cp_async16(dst + 128 * q + 4 * lane, src + 128 * q + 4 * lane);
+        cp_async_commit();
+    };
+    if (n_chunks > 0) stage_chunk(0);
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        if (chunk + 1 < n_chunks) {
+            stage_chunk(chunk + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const int* src = stage + (chunk & 1) * (CH * 32) + lane;
+        const int n_in = min(CH, n_iter - chunk * CH);
+        for (int i = 0; i < n_in; i += NU, src += 32 * NU) {
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const int jk = src[32 * u];
+                const unsigned char* pj = snb + (jk & 0xffff);
+                const unsigned char* pk = snb + ((unsigned)jk >> 16);
+                const float4 j0 = lds128f(pj), j1 = lds128f(pj + 16);  // [d_x d_y d_z r^2 | 1/r W Q -]
+                const float4 k0 = lds128f(pk), k1 = lds128f(pk + 16);
+                const float ex = j0.x - k0.x, ey = j0.y - k0.y, ez = j0.z - k0.z;
+                const float rjk2 = fmaxf(fmaf(ez, ez, fmaf(ey, ey, ex * ex)), 1e-30f);
+                const float rjk = rjk2 * rsqf(rjk2);
+                const float cost = fmaf(j0.z, k0.z, fmaf(j0.y, k0.y, j0.x * k0.x)) * (j1.x * k1.x);
+                // tanh(x) = 1 - 2 / (exp(2x) + 1), 2x = 2 - 2 r_jk / rc clamped at 0: exactly 0 at and beyond the cutoff
+                const float x2 = fmaxf(fmaf(rjk, m2l_inv_rc, two_l2e), 0.0f);
+                const float th = fmaf(-2.0f, rcpf(ex2f(x2) + 1.0f), 1.0f);
+                const float g = ex2f(neta_l2e * rjk2);
+                const float bs = fmaf(lam, cost, 1.0f);
+                float ep = (j1.y * k1.y) * ((th * th) * (th * g));
+                if (ZM1 == 1) ep *= bs;
+                else if (ZM1 == 3) ep *= bs * (bs * bs);
+                else if (ZM1 < 0) ep *= powi<float>(bs, zm1_rt);
+                const float ap = bs * ep;
+                aG[u] += ap;
+                const float Tc = zl * ep;
+                // gradient coefficients on the difference vectors: (B / r) d
+                const float Bj = fmaf(Tc, fmaf(-cost, j1.x, k1.x), ap * j1.z) * j1.x;
+                const float Bk = fmaf(Tc, fmaf(-cost, k1.x, j1.x), ap * k1.z) * k1.x;
+                aX[u] = fmaf(Bk, k0.x, fmaf(Bj, j0.x, aX[u]));
+                aY[u] = fmaf(Bk, k0.y, fmaf(Bj, j0.y, aY[u]));
+                aZ[u] = fmaf(Bk, k0.z, fmaf(Bj, j0.z, aZ[u]));
+            }
+        }
+        __syncwarp();
+    }
+    double dG = 0, dX = 0, dY = 0, dZ = 0;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) { dG += (double)aG[u]; dX += (double)aX[u]; dY += (double)aY[u]; dZ += (double)aZ[u]; }
+    oG = warp_sum(dG); oX = warp_sum(dX); oY = warp_sum(dY); oZ = warp_sum(dZ);
+}
+
+__global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2F_MINBLOCKS) hdnnp_eval2f_kernel(const AtomArgs<double> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    __shared__ __align__(16) int s_stage[kEvalWarps][2 * kChunk2 * 32];
+    const int w = blockIdx.x * kEvalWarps + wib;
+    if (w >= a.n_work) return;
+    int slot, out_row, etype;
+    if (!resolve_item(a, w, slot, out_row, etype)) return;
+    if (etype >= a.n_types) return;
+    const ElementTable& tab = a.tables[etype];
+    const int n_sf = tab.n_sf;
+    const Rec<double> ri = a.rec[slot];
+    double lx, ly, lz;
+    bool pbc;
+    item_box(a, slot, lx, ly, lz, pbc);
+    constexpr float kL2E = 1.4426950408889634f;
+
+    const int cap = a.scap;
+    const size_t per_atom = eval2f_smem_bytes(cap, a.n_sf_max);
+    unsigned char* snb = smem_raw + (size_t)wib * per_atom;                     // [cap + 1] records of 48 bytes
+    double* sacc = (double*)(snb + (((size_t)(cap + 1) * kRec2fBytes + 7) & ~size_t(7)));  // [n_sf_max][4]
+
+    Segments sg;
+    sg.load(a.tcount + (size_t)slot * kBuckets, cap);
+    const int total = sg.total;
+    if (sg.seg[kBuckets] > cap && lane == 0) atomicMax(&a.flags[1], sg.seg[kBuckets]);
+
+    // ---- stage the neighbour block: gathers and differences in double, records in single -------------------------
+    {
+        const int32_t* row = a.nbr + (size_t)slot * a.cap;
+        const bool has_cls = tab.n_cls > 0;
+        const int ct = has_cls ? tab.cls[0].type : PANTEA_CUT_HARD;
+        const float rcc = has_cls ? (float)tab.cls[0].rc : 1.0f;
+        const float irc = 1.0f / rcc;
+        constexpr int RB = 5;
+        for (int base = 0; base < total; base += 32 * RB) {
+            int idx[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int n = base + 32 * r + lane;
+                idx[r] = row[n < total ? n : total - 1];
+            }
+            Rec<double> rr[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) rr[r] = a.rec[idx[r]];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int n = base + 32 * r + lane;
+                if (n < total) {
+                    double ddx = sub_rn(ri.x, rr[r].x), ddy = sub_rn(ri.y, rr[r].y), ddz = sub_rn(ri.z, rr[r].z);
+                    if (pbc) { ddx = min_image(ddx, lx); ddy = min_image(ddy, ly); ddz = min_image(ddz, lz); }
+                    const float dx = (float)ddx, dy = (float)ddy, dz = (float)ddz;
+                    const int ntype = rr[r].type;
+                    const float r2n = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    const float iv = rsqf(r2n), rad = r2n * iv;
+                    float fc, q;
+                    if (ct == PANTEA_CUT_TANHU) {
+                        const float t = fmaf(-2.0f, rcpf(ex2f(fmaxf(fmaf(-2.0f * kL2E * irc, rad, 2.0f * kL2E), 0.0f)) + 1.0f), 1.0f);
+                        const bool in = rad < rcc && t > 0.0f;
+                        fc = in ? t * t * t : 0.0f;
+                        q = in ? -3.0f * irc * (1.0f - t * t) * rcpf(t) : 0.0f;
+                    } else {
+                        float dfc;
+                        cutoff_eval_ool<float>(ct, rad, rcc, &fc, &dfc);
+                        q = fc != 0.0f ? dfc / fc : 0.0f;
+                    }
+                    const float eta_t = (float)tab.v2_eta[ntype], ws_t = (float)tab.v2_wscale[ntype];
+                    const float W = ws_t * fc * ex2f(fmaxf(-eta_t * kL2E * r2n, -120.0f));
+                    const float Q = fmaf(-2.0f * eta_t, rad, q);
+                    float4* p = (float4*)(snb + (size_t)n * kRec2fBytes);
+                    p[0] = make_float4(dx, dy, dz, r2n);
+                    p[1] = make_float4(iv, W, Q, 0.0f);
+                    p[2] = make_float4(fc, q, 0.0f, 0.0f);
+                }
+            }
+        }
+        // the record pad entries point at: W = 0 makes every term vanish, d = (1, 0, 0) keeps r_jk and 1/r finite
+        if (lane < 3) ((float4*)(snb + (size_t)total * kRec2fBytes))[lane] = lane == 0 ? make_float4(0.f, 0.f, 0.f, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+
+    // ---- radial symmetry functions -----------------------------------------------------------------------------------
+    for (int s = 0; s < tab.n_radial; ++s) {
+        const RadialSF sf = tab.radial[s];
+        const int lo = sg.lo(sf.type_j), hi = sg.hi(sf.type_j);
+        const float eta = (float)sf.eta, rs = (float)sf.r_shift;
+        float g = 0, gx = 0, gy = 0, gz = 0;
+        for (int n = lo + lane; n < hi; n += 32) {
+            const float4* p = (const float4*)(snb + (size_t)n * kRec2fBytes);
+            const float4 p0 = p[0], p1 = p[1], p2 = p[2];
+            const float r = p0.w * p1.x, fc = p2.x, q = p2.y;
+            float val, dval;
+            if (sf.kind == PANTEA_G1) { val = fc; dval = fc * q; }
+            else {
+                const float dr = r - rs, ex = ex2f(fmaxf(-eta * kL2E * dr * dr, -120.0f));
+                val = ex * fc; dval = val * (q - 2.0f * eta * dr);
+            }
+            g += val;
+            dval *= p1.x;  // on the difference vector: (dval / r) d
+            gx += dval * p0.x; gy += dval * p0.y; gz += dval * p0.z;
+        }
+        const double G = warp_sum((double)g), X = warp_sum((double)gx), Y = warp_sum((double)gy), Z = warp_sum((double)gz);
+        if (lane == 0) { double* o = sacc + 4 * sf.out; o[0] = G; o[1] = X; o[2] = Y; o[3] = Z; }
+    }
+
+    // ---- angular symmetry functions ----------------------------------------------------------------------------------
+    {
+        const int32_t* offs = a.pair_off + (size_t)w * (a.max_groups + 1);
+        const int32_t* lists = a.pairs + (size_t)w * a.pair_cap;
+        int* stage = s_stage[wib];
+        for (int gi = 0; gi < tab.n_groups; ++gi) {
+            const AngularGroup grp = tab.groups[gi];
+            const AngularMember mem = tab.members[grp.first];
+            const int lo = offs[gi], n_iter = (offs[gi + 1] - lo) >> 5;
+            const float rc = (float)tab.cls[grp.cls].rc;
+            const float zl = (float)(mem.zeta * mem.lambda0), neta = (float)(-mem.eta) * kL2E, lam = (float)mem.lambda0;
+            double G, X, Y, Z;
+            if (mem.izeta == 1) angular2f<0>(snb, lists + lo, n_iter, neta, lam, zl, 0, rc, lane, stage, G, X, Y, Z);
+            else if (mem.izeta == 2) angular2f<1>(snb, lists + lo, n_iter, neta, lam, zl, 1, rc, lane, stage, G, X, Y, Z);
+            else if (mem.izeta == 4) angular2f<3>(snb, lists + lo, n_iter, neta, lam, zl, 3, rc, lane, stage, G, X, Y, Z);
+            else angular2f<-1>(snb, lists + lo, n_iter, neta, lam, zl, mem.izeta - 1, rc, lane, stage, G, X, Y, Z);
+            if (lane == 0) { double* o = sacc + 4 * mem.out; o[0] = G; o[1] = X; o[2] = Y; o[3] = Z; }
+        }
+    }
+    __syncwarp();
+    if (a.G)
+        for (int s = lane; s < n_sf; s += 32) a.G[(size_t)out_row * a.g_stride + s] = sacc[4 * s];
+    if (a.dG)
+        for (int e = lane; e < n_sf * 3; e += 32) {
+            const int s = e / 3, c = e - 3 * s;
+            a.dG[((size_t)out_row * a.g_stride + s) * 3 + c] = sacc[4 * s + 1 + c];
+        }
+    if (a.gbuf)
+        for (int e = lane; e < n_sf * 4; e += 32) a.gbuf[(size_t)w * a.n_sf_max * 4 + e] = sacc[e];
+}
+
+// ------------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------------
 static int g_time_eval = 0;
@@ -672,15 +906,19 @@ int launch_v2(const AtomArgs<double>& a, cudaStream_t st) {
         pair_filter2_kernel<double><<<blocks, kFilter2Warps * 32, smem, st>>>(a);
         PANTEA_LAUNCH_CHECK();
     }
-    const size_t smem = (size_t)kEvalWarps * eval2_smem_bytes(a.scap, a.n_sf_max);
-    int rc = opt_in_smem((const void*)hdnnp_eval2_kernel, smem, conf_eval, "evaluation: neighbour capacity too large for shared memory");
+    const bool single = a.rec_bytes == kRec2fBytes;
+    static size_t conf_evalf[64] = {0};
+    const size_t smem = (size_t)kEvalWarps * (single ? eval2f_smem_bytes(a.scap, a.n_sf_max) : eval2_smem_bytes(a.scap, a.n_sf_max));
+    int rc = single ? opt_in_smem((const void*)hdnnp_eval2f_kernel, smem, conf_evalf, "evaluation: neighbour capacity too large for shared memory")
+                    : opt_in_smem((const void*)hdnnp_eval2_kernel, smem, conf_eval, "evaluation: neighbour capacity too large for shared memory");
     if (rc != PANTEA_OK) return rc;
     const int blocks = (a.n_work + kEvalWarps - 1) / kEvalWarps;
     if (g_time_eval) {  // measurement hook (pantea_eval_timing): CUDA events around the dominant kernel, not capturable
         if (!g_ev0) { PANTEA_CUDA_TRY(cudaEventCreate(&g_ev0)); PANTEA_CUDA_TRY(cudaEventCreate(&g_ev1)); }
         PANTEA_CUDA_TRY(cudaEventRecord(g_ev0, st));
     }
-    hdnnp_eval2_kernel<<<blocks, kEvalWarps * 32, smem, st>>>(a);
+    if (single) hdnnp_eval2f_kernel<<<blocks, kEvalWarps * 32, smem, st>>>(a);
+    else hdnnp_eval2_kernel<<<blocks, kEvalWarps * 32, smem, st>>>(a);
     PANTEA_LAUNCH_CHECK();
     if (g_time_eval) PANTEA_CUDA_TRY(cudaEventRecord(g_ev1, st));
     return PANTEA_OK;

@@ -150,6 +150,7 @@ struct pantea_workspace {
     int pair_cap = 0, pair_groups = 0, pair_cap_request = 0;
     int smem_cap = 0;  // rows staged in shared memory by the atom kernel (0: cap); set from the observed maximum
     int dtype = PANTEA_F64;
+    bool compute32 = false;  // mixed mode: symmetry functions in single precision on double-precision state (fast path only)
     int n_types = 0;  // buckets used by the potential (others -> bucket n_types)
 
     // current binding

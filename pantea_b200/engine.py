@@ -168,6 +168,12 @@ class Workspace:
         self.skin = float(skin)
         _lib.check(_lib.load().pantea_workspace_set_skin(self.handle, self.skin))
 
+    def set_compute_precision(self, bits: int) -> None:
+        """32: mixed mode of a float64 workspace -- symmetry functions in single precision on double-precision state
+        (difference vectors still formed in double); 64: everything double (default)."""
+        _lib.check(_lib.load().pantea_workspace_set_compute_precision(self.handle, int(bits)))
+        self.compute_bits = int(bits)
+
     def rebuild_counts(self) -> Tuple[int, int]:
         """(neighbour builds that ran with a skin, how many of them rebuilt the rows)."""
         out = (C.c_int64 * 2)()

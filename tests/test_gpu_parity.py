@@ -563,3 +563,50 @@ def test_coincident_neighbours_are_excluded_exactly(n_atoms, pot):
     _, ea_o, f_o = c_oracle.energy_forces(pot, pos, types, box)
     assert rel_err(e_atom.cpu().numpy(), ea_o) < 1e-10
     assert rel_err(f.cpu().numpy(), f_o) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------ fast path / mixed precision
+@pytest.mark.parametrize("n_atoms", [12000, 99999])
+def test_fast_path_and_mixed_precision_against_oracle(n_atoms, pot):
+    """Specialised kernels (csrc/acsf2.cu) on the configurations they serve: double evaluation <= 1e-10 against the
+    oracle with and without Gaussian screening, identical neighbour handling as the generic kernels; mixed mode (FP32
+    symmetry functions on FP64 state, pantea_workspace_set_compute_precision) <= 1e-5 -- element-wise with the rms force
+    as the absolute floor."""
+    from pantea_b200 import _lib
+    lib = _lib.load()
+    pos, types, box = water_box(n_atoms)
+    dev = device_potential_from_specs(pot)
+    ws = _workspace(dev, n_atoms)
+    ws.bind(cuda(pos), cuda(types, torch.int32), box, dev.r_cutoff)
+    m = min(n_atoms, 6000)
+    _, ea_o, f_o = c_oracle.energy_forces(pot, pos, types, box, begin=0, end=m)
+    f_o = torch.as_tensor(f_o[:m], device="cuda")
+    rms = float(f_o.pow(2).mean().sqrt())
+
+    def err_over(f, rtol):
+        return float(((f[:m] - f_o).abs() / (rtol * (f_o.abs() + rms))).max())
+
+    try:
+        lib.pantea_set_fast_path(0)
+        _, _, f_gen = ws.energy_forces(False, True)
+        f_gen = f_gen.clone()
+        lib.pantea_set_fast_path(1)
+        old = lib.pantea_set_gauss_screen(0.0)
+        _, e_atom, f_fast = ws.energy_forces(False, True, True)
+        f_fast, e_fast = f_fast.clone(), e_atom.clone()
+        lib.pantea_set_gauss_screen(40.0)
+        _, e_atom, f_scr = ws.energy_forces(False, True, True)
+        f_scr, e_scr = f_scr.clone(), e_atom.clone()
+        ws.set_compute_precision(32)
+        _, _, f_mix = ws.energy_forces(False, True)
+        f_mix = f_mix.clone()
+    finally:
+        ws.set_compute_precision(64)
+        lib.pantea_set_fast_path(1)
+        lib.pantea_set_gauss_screen(40.0)
+    assert err_over(f_gen, 1e-10) <= 1.0
+    assert err_over(f_fast, 1e-10) <= 1.0
+    assert err_over(f_scr, 1e-10) <= 1.0
+    assert rel_err(e_fast[:m].cpu().numpy(), ea_o[:m]) < 1e-10 and rel_err(e_scr[:m].cpu().numpy(), ea_o[:m]) < 1e-10
+    assert float((f_scr - f_fast).abs().max()) < 1e-13 * float(f_fast.abs().max())  # what screening drops is below 1e-14 of G
+    assert err_over(f_mix, 1e-5) <= 1.0

@@ -72,6 +72,12 @@ print(f"n={n} generic E={e0:.12f} fast E={e1:.12f} dE/E={abs(e1 - e0) / abs(e0):
 print(f"fast vs generic forces: max elementwise rel {rel.max().item():.3e}, max abs {(f1 - f0).abs().max().item():.3e}, "
       f"max|F| {f0.abs().max().item():.3e}; e_atom max abs {(ea1 - ea0).abs().max().item():.3e}")
 print(f"force evaluation: generic {timed(False):.4f} ms, fast {timed(True):.4f} ms")
+ws.set_compute_precision(32)
+e3, ea3, f3 = forces(True)
+rms = float(f0.pow(2).mean().sqrt())
+print(f"mixed (FP32 symmetry functions) vs generic: max |dF| / (|F| + rms) {((f3 - f0).abs() / (f0.abs() + rms)).max().item():.3e}, "
+      f"dE/E {abs(e3 - e0) / abs(e0):.2e}; force evaluation {timed(True):.4f} ms")
+ws.set_compute_precision(64)
 if n_oracle > 0:
     from oracle import c_oracle
     from oracle.spec import load_potential
@@ -85,8 +91,9 @@ if n_oracle > 0:
         r = ((f[:m] - f_o).abs() / f_o.abs().clamp_min(1e-300)).max().item()
         print(f"{name} vs oracle: max elementwise rel {r:.3e}, max abs {(f[:m] - f_o).abs().max().item():.3e}")
 from torch.profiler import ProfilerActivity, profile
-for fast in (False, True):
+for fast in (False, True, 32):
     lib.pantea_set_fast_path(1 if fast else 0)
+    ws.set_compute_precision(32 if fast == 32 else 64)
     f = torch.zeros((n, 3), dtype=torch.float64, device=dev)
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(5):
@@ -94,5 +101,6 @@ for fast in (False, True):
             _lib.check(lib.pantea_energy_forces(ws.handle, None, _lib.ptr(f), None, 0, _lib.stream_ptr()))
         torch.cuda.synchronize()
     for ev in sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:6]:
-        print(f"[{'fast' if fast else 'generic'}] {ev.key[:60]:60s} n={ev.count:3d} avg={ev.device_time_total / ev.count / 1e3:8.4f} ms")
+        print(f"[{'mixed32' if fast == 32 else 'fast' if fast else 'generic'}] {ev.key[:60]:60s} n={ev.count:3d} avg={ev.device_time_total / ev.count / 1e3:8.4f} ms")
 lib.pantea_set_fast_path(1)
+ws.set_compute_precision(64)
