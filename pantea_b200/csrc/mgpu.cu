@@ -120,6 +120,7 @@ __global__ void mgpu_integrate_push_kernel(int n, const uint8_t* __restrict__ ro
         for (int d = 0; d < 3; ++d) { s_lo[r][d] = bt.edges[d][c[d]]; s_hi[r][d] = bt.edges[d][c[d] + 1]; }
     }
     __syncthreads();
+    int wrote_remote = 0;
     if (id < n && role[id] == 2) {
         const T* vel = (const T*)pt.vel[bt.rank];
         const T* frc = (const T*)pt.frc[bt.rank];
@@ -141,6 +142,7 @@ __global__ void mgpu_integrate_push_kernel(int n, const uint8_t* __restrict__ ro
                 if (bt.dims[d] > 1 && axis_gap((double)x[d], s_lo[r][d], s_hi[r][d], bt.box[d]) > bt.reach) inside = false;
             if (!inside) continue;
             ((MailRec<T>*)pt.mail[r])[(size_t)(next & 1) * n + id] = m;  // NVLink store when r is a peer
+            wrote_remote |= r != bt.rank;
             if (r == owner && r != bt.rank) {  // the atom changes its owner: velocity and force rows travel with it
                 T* pv = (T*)pt.vel[r];
                 T* pf = (T*)pt.frc[r];
@@ -151,9 +153,10 @@ __global__ void mgpu_integrate_push_kernel(int n, const uint8_t* __restrict__ ro
     }
     // publish: the block's stores are ordered before its ticket (barrier, then one cumulative system-scope fence), the
     // last block raises the flags
-    __syncthreads();
+    const int any_remote = __syncthreads_or(wrote_remote);
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        if (any_remote) __threadfence_system();  // (a block without peer stores has nothing to order across the links)
+        else __threadfence();
         const unsigned int t = atomicAdd(done, 1u);
         if (t == gridDim.x - 1) {
             *done = 0;
@@ -283,7 +286,7 @@ size_t esize(int dtype) { return dtype == PANTEA_F64 ? 8 : 4; }
 template <typename T>
 int mgpu_step_typed(pantea_mgpu* mg, cudaStream_t st) {
     const int n = (int)mg->n, threads = 256, blocks = (n + threads - 1) / threads;
-    mgpu_integrate_push_kernel<T><<<blocks, threads, 0, st>>>(n, mg->role, (const T*)mg->pos, mg->bt_dev, mg->pt_dev, mg->epoch,
+    mgpu_integrate_push_kernel<T><<<(n + 511) / 512, 512, 0, st>>>(n, mg->role, (const T*)mg->pos, mg->bt_dev, mg->pt_dev, mg->epoch,
                                                               (T)mg->dt, mg->done);
     PANTEA_LAUNCH_CHECK();
     mgpu_wait_unpack_kernel<T><<<blocks, threads, 0, st>>>(n, mg->role, (T*)mg->pos, mg->bt_dev, mg->pt_dev, mg->epoch, 1,
