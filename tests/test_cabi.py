@@ -44,6 +44,10 @@ def test_error_convention_without_gpu():
     assert lib.pantea_workspace_create(None, 64, 32, 16, ctypes.byref(handle)) == _lib.PANTEA_EINVAL
     with pytest.raises(ValueError):
         _lib.check(lib.pantea_workspace_set_owned_range(None, 0, 1))
+    # process-wide switches are plain setters (no device needed) and return the previous value
+    assert lib.pantea_set_fast_path(0) == 1 and lib.pantea_set_fast_path(1) == 0
+    assert lib.pantea_set_gauss_screen(0.0) == 40.0 and lib.pantea_set_gauss_screen(40.0) == 0.0
+    assert lib.pantea_mgpu_handle_bytes() == 64 and lib.pantea_mgpu_destroy(None) == 0
     # argument validation of the later entry points happens before any CUDA call
     counts = (ctypes.c_int64 * 2)()
     stats = ctypes.c_void_p(16)  # never dereferenced: the checks below fail first
@@ -61,7 +65,14 @@ def test_error_convention_without_gpu():
             (lambda: lib.pantea_md_update_positions_mass(None, None, None, None, 0, 4, None, 0.25, 64, None), b"NULL argument"),
             (lambda: lib.pantea_md_update_velocities_mass(stats, stats, stats, None, 0, 4, 0.25, 7, None), b"dtype"),
             (lambda: lib.pantea_energy_forces(None, None, None, None, 1, None), b"no potential"),
-            (lambda: lib.pantea_neighbor_build(None, None, None, 0, None, 1.0, None), b"NULL argument")):
+            (lambda: lib.pantea_neighbor_build(None, None, None, 0, None, 1.0, None), b"NULL argument"),
+            (lambda: lib.pantea_workspace_set_compute_precision(None, 32), b"NULL workspace"),
+            (lambda: lib.pantea_mgpu_create(None, 0, 1, 10, None, None, None, None, None, 12.0, 0.25, 0, ctypes.byref(handle)), b"NULL argument"),
+            (lambda: lib.pantea_mgpu_connect(None, None), b"NULL argument"),
+            (lambda: lib.pantea_mgpu_set_state(None, None, None, None, None), b"NULL argument"),
+            (lambda: lib.pantea_mgpu_run(None, 1, 1, None), b"NULL argument"),
+            (lambda: lib.pantea_mgpu_read(None, None, None, None, None, None, None), b"NULL argument"),
+            (lambda: lib.pantea_mgpu_export_handle(None, None), b"NULL argument")):
         code = call()
         assert code == _lib.PANTEA_EINVAL and needle in lib.pantea_last_error(), (code, lib.pantea_last_error())
 

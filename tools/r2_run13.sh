@@ -1,5 +1,2 @@
-out=gpurun_out/r2_h
-mkdir -p $out
-timeout 900 python -m pytest tests -m gpu -q -x > $out/pytest_gpu.log 2>&1; tail -4 $out/pytest_gpu.log
-timeout 300 python tools/brick_profile.py 99999 20 2>&1 | grep -v "Warn\|warn" | head -9
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29515 tools/brick_profile.py 99999 20 2>&1 | grep -v "Warn\|warn\|\*\*\*\|OMP" | head -10
+timeout 300 python tools/brick_profile.py 99999 20 2>&1 | grep -v "Warn\|warn" | head -5
+timeout 300 python tests/mgpu_check.py 99999 10 brick oracle 2>&1 | tail -1
