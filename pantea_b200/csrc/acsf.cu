@@ -584,7 +584,15 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_force_kernel(const AtomArgs<T
                 for (int i = 0; i < ni; ++i) z += sh[(in_off + i) * kMlpThreads] * (T)W[(size_t)i * no + o];
                 z += (T)B[o];
                 T y, dy;
-                activation_eval_ool<T>(act, z, &y, &dy);
+                if (act == PANTEA_ACT_TANH) {
+                    // inline tanh(z) = sign(z) (1 - 2 / (exp(2|z|) + 1)): the library routine is ~150 instructions of a
+                    // kernel that is a serial chain per atom (latency-bound when a rank owns ~10^4 atoms); abs. error 1e-16
+                    const T az = z < (T)0 ? -z : z;
+                    const T t = az < (T)20 ? (T)1 - (T)2 * fast_rcp(fast_exp((T)2 * az) + (T)1) : (T)1;
+                    y = z < (T)0 ? -t : t; dy = (T)1 - t * t;
+                } else {
+                    activation_eval_ool<T>(act, z, &y, &dy);
+                }
                 sh[(out_off + o) * kMlpThreads] = y;
                 sdact[(out_off - n_sf + o) * kMlpThreads] = dy;
             }

@@ -32,6 +32,26 @@ constexpr int kTab2 = 256;                // entries of the 2^(i/256) table
 #endif
 constexpr int kChunk2 = PANTEA_CHUNK2;    // pair-list iterations per cp.async group (4 or 8)
 constexpr int kFilter2Warps = 8;
+
+// Atoms per block of the evaluation / filter kernels: the warps of a block draw the block's atoms from a shared counter
+// one after the other.  With one atom per warp the block lives as long as its most expensive atom (an O centre walks
+// twice the triplets of an H centre) while the other warps' slots idle: 32 % of the warp time of the water benchmark.
+#ifndef PANTEA_ATOMS_PER_WARP
+#define PANTEA_ATOMS_PER_WARP 4
+#endif
+constexpr int kAtomsPerWarp = PANTEA_ATOMS_PER_WARP;
+#ifndef PANTEA_FILTER_ATOMS_PER_WARP
+#define PANTEA_FILTER_ATOMS_PER_WARP 1  // the filter's atoms differ less in cost; dynamic assignment measured slower
+#endif
+constexpr int kFilterAtomsPerWarp = PANTEA_FILTER_ATOMS_PER_WARP;
+
+__device__ __forceinline__ int next_item(int* counter, int lane) {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(counter, 1);
+    return __shfl_sync(kFullMask, v, 0);
+}
+
+
 #ifndef PANTEA_NU2
 #define PANTEA_NU2 2
 #endif
@@ -271,11 +291,7 @@ struct Filter2 {
 #define PANTEA_FILTER2_MINBLOCKS 3
 #endif
 template <typename T>
-__global__ void __launch_bounds__(kFilter2Warps * 32, PANTEA_FILTER2_MINBLOCKS) pair_filter2_kernel(const AtomArgs<T> a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    if (a.filter_guard && *a.filter_guard == 0) return;  // rows unchanged since the lists were written
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int w = blockIdx.x * kFilter2Warps + wib;
+__device__ __forceinline__ void filter2_atom(const AtomArgs<T>& a, int w, int lane, int wib, unsigned char* smem_raw) {
     if (w >= a.n_work) return;
     int slot, out_row, etype;
     if (!resolve_item(a, w, slot, out_row, etype)) return;
@@ -418,6 +434,24 @@ __global__ void __launch_bounds__(kFilter2Warps * 32, PANTEA_FILTER2_MINBLOCKS) 
         atomicMax(&a.flags[2], f.off);
         if (a.counters) atomicAdd(&a.counters[3], (unsigned long long)n_real);  // list entries the evaluation will walk
     }
+    __syncwarp();  // the warp's staging array and strip are reused by its next atom
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFilter2Warps * 32, PANTEA_FILTER2_MINBLOCKS) pair_filter2_kernel(const AtomArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.filter_guard && *a.filter_guard == 0) return;  // rows unchanged since the lists were written
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (kFilterAtomsPerWarp == 1) {  // one atom per warp, no counter
+        filter2_atom<T>(a, blockIdx.x * kFilter2Warps + wib, lane, wib, smem_raw);
+        return;
+    }
+    __shared__ int s_next;
+    if (threadIdx.x == 0) s_next = 0;
+    __syncthreads();
+    constexpr int per_block = kFilter2Warps * kFilterAtomsPerWarp;
+    for (int k = next_item(&s_next, lane); k < per_block; k = next_item(&s_next, lane))
+        filter2_atom<T>(a, blockIdx.x * per_block + k, lane, wib, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -517,14 +551,8 @@ __device__ __forceinline__ void angular2(const unsigned char* __restrict__ snb, 
     oG = warp_sum(aG[0]); oX = warp_sum(aX[0]); oY = warp_sum(aY[0]); oZ = warp_sum(aZ[0]);
 }
 
-__global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2_MINBLOCKS) hdnnp_eval2_kernel(const AtomArgs<double> a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    __shared__ double s_etab[kTab2];
-    for (int i = threadIdx.x; i < kTab2; i += blockDim.x) s_etab[i] = exp2((double)i * (1.0 / kTab2));
-    __shared__ __align__(16) int s_stage[kEvalWarps][2 * kChunk2 * 32];
-    __syncthreads();
-    const int w = blockIdx.x * kEvalWarps + wib;
+__device__ __forceinline__ void eval2_atom(const AtomArgs<double>& a, int w, int lane, int wib, unsigned char* smem_raw,
+                                           const double* __restrict__ s_etab, int* stage) {
     if (w >= a.n_work) return;
     int slot, out_row, etype;
     if (!resolve_item(a, w, slot, out_row, etype)) return;
@@ -634,7 +662,6 @@ __global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2_MINBLOCKS) hdnnp
     {
         const int32_t* offs = a.pair_off + (size_t)w * (a.max_groups + 1);
         const int32_t* lists = a.pairs + (size_t)w * a.pair_cap;
-        int* stage = s_stage[wib];
         for (int gi = 0; gi < tab.n_groups; ++gi) {
             const AngularGroup grp = tab.groups[gi];
             const AngularMember mem = tab.members[grp.first];
@@ -659,6 +686,21 @@ __global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2_MINBLOCKS) hdnnp
         }
     if (a.gbuf)
         for (int e = lane; e < n_sf * 4; e += 32) a.gbuf[(size_t)w * a.n_sf_max * 4 + e] = sacc[e];
+    __syncwarp();  // the warp's shared-memory regions are reused by its next atom
+}
+
+__global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2_MINBLOCKS) hdnnp_eval2_kernel(const AtomArgs<double> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    __shared__ double s_etab[kTab2];
+    for (int i = threadIdx.x; i < kTab2; i += blockDim.x) s_etab[i] = exp2((double)i * (1.0 / kTab2));
+    __shared__ __align__(16) int s_stage[kEvalWarps][2 * kChunk2 * 32];
+    __shared__ int s_next;
+    if (threadIdx.x == 0) s_next = 0;
+    __syncthreads();
+    constexpr int per_block = kEvalWarps * kAtomsPerWarp;
+    for (int k = next_item(&s_next, lane); k < per_block; k = next_item(&s_next, lane))
+        eval2_atom(a, blockIdx.x * per_block + k, lane, wib, smem_raw, s_etab, s_stage[wib]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -754,11 +796,7 @@ __device__ __forceinline__ void angular2f(const unsigned char* __restrict__ snb,
     oG = warp_sum(dG); oX = warp_sum(dX); oY = warp_sum(dY); oZ = warp_sum(dZ);
 }
 
-__global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2F_MINBLOCKS) hdnnp_eval2f_kernel(const AtomArgs<double> a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    __shared__ __align__(16) int s_stage[kEvalWarps][2 * kChunk2 * 32];
-    const int w = blockIdx.x * kEvalWarps + wib;
+__device__ __forceinline__ void eval2f_atom(const AtomArgs<double>& a, int w, int lane, int wib, unsigned char* smem_raw, int* stage) {
     if (w >= a.n_work) return;
     int slot, out_row, etype;
     if (!resolve_item(a, w, slot, out_row, etype)) return;
@@ -863,7 +901,6 @@ __global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2F_MINBLOCKS) hdnn
     {
         const int32_t* offs = a.pair_off + (size_t)w * (a.max_groups + 1);
         const int32_t* lists = a.pairs + (size_t)w * a.pair_cap;
-        int* stage = s_stage[wib];
         for (int gi = 0; gi < tab.n_groups; ++gi) {
             const AngularGroup grp = tab.groups[gi];
             const AngularMember mem = tab.members[grp.first];
@@ -888,6 +925,19 @@ __global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2F_MINBLOCKS) hdnn
         }
     if (a.gbuf)
         for (int e = lane; e < n_sf * 4; e += 32) a.gbuf[(size_t)w * a.n_sf_max * 4 + e] = sacc[e];
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2F_MINBLOCKS) hdnnp_eval2f_kernel(const AtomArgs<double> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    __shared__ __align__(16) int s_stage[kEvalWarps][2 * kChunk2 * 32];
+    __shared__ int s_next;
+    if (threadIdx.x == 0) s_next = 0;
+    __syncthreads();
+    constexpr int per_block = kEvalWarps * kAtomsPerWarp;
+    for (int k = next_item(&s_next, lane); k < per_block; k = next_item(&s_next, lane))
+        eval2f_atom(a, blockIdx.x * per_block + k, lane, wib, smem_raw, s_stage[wib]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -902,7 +952,7 @@ int launch_v2(const AtomArgs<double>& a, cudaStream_t st) {
         const size_t smem = (size_t)kFilter2Warps * ((a.scap + 32) * sizeof(float4) + kStrip2 * sizeof(int32_t));
         int rc = opt_in_smem((const void*)pair_filter2_kernel<double>, smem, conf_filter, "pair filter: neighbour capacity too large for shared memory");
         if (rc != PANTEA_OK) return rc;
-        const int blocks = (a.n_work + kFilter2Warps - 1) / kFilter2Warps;
+        const int blocks = (a.n_work + kFilter2Warps * kFilterAtomsPerWarp - 1) / (kFilter2Warps * kFilterAtomsPerWarp);
         pair_filter2_kernel<double><<<blocks, kFilter2Warps * 32, smem, st>>>(a);
         PANTEA_LAUNCH_CHECK();
     }
@@ -912,7 +962,7 @@ int launch_v2(const AtomArgs<double>& a, cudaStream_t st) {
     int rc = single ? opt_in_smem((const void*)hdnnp_eval2f_kernel, smem, conf_evalf, "evaluation: neighbour capacity too large for shared memory")
                     : opt_in_smem((const void*)hdnnp_eval2_kernel, smem, conf_eval, "evaluation: neighbour capacity too large for shared memory");
     if (rc != PANTEA_OK) return rc;
-    const int blocks = (a.n_work + kEvalWarps - 1) / kEvalWarps;
+    const int blocks = (a.n_work + kEvalWarps * kAtomsPerWarp - 1) / (kEvalWarps * kAtomsPerWarp);
     if (g_time_eval) {  // measurement hook (pantea_eval_timing): CUDA events around the dominant kernel, not capturable
         if (!g_ev0) { PANTEA_CUDA_TRY(cudaEventCreate(&g_ev0)); PANTEA_CUDA_TRY(cudaEventCreate(&g_ev1)); }
         PANTEA_CUDA_TRY(cudaEventRecord(g_ev0, st));
