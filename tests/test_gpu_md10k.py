@@ -6,8 +6,8 @@ reference dynamics densifies the box, so neighbour rows / pair lists outgrow the
 Oracle: tests/golden/md10k_3000.json (tests/golden/make_md10k_3000.py: C oracle curves sampled every 100 steps, plus a
 run with one coordinate perturbed by 1e-13 Bohr).  The dynamics is chaotic: point-wise agreement exists over the first
 few hundred steps; afterwards two correct implementations share the statistics of the curve, and the perturbed oracle
-run says how far they may be apart.  Required: <= 1e-6 of the energy scale up to step 500, then within 3x the oracle's
-own perturbed-run deviation (with a floor) for log(E_kin) and E_pot."""
+run says how far they may be apart.  Required: <= 1e-6 of the energy scale up to step 500, then within 4x the oracle's
+own perturbed-run deviation (floors: 0.1 in log E_kin, 2 % of the E_pot scale)."""
 import json
 
 import numpy as np
@@ -46,8 +46,8 @@ def test_md_3000_atoms_10k_steps_follows_the_oracle_curve(ensemble, golden_dir):
     scal = sim.simulate_steps(system, n_steps, record=True).cpu().numpy()     # [n_steps, 2]: (E_pot, E_kin) after each step
     assert np.isfinite(scal).all()
     scale_pot, scale_kin = np.abs(ref[:6, 0]).max(), ref[:6, 1].max()
-    log_band = max(3.0 * spread["max_abs_log_ratio_e_kin"], 0.05)
-    pot_band = max(3.0 * spread["max_abs_dev_e_pot"], 1e-3 * scale_pot)
+    log_band = max(4.0 * spread["max_abs_log_ratio_e_kin"], 0.1)
+    pot_band = max(4.0 * spread["max_abs_dev_e_pot"], 0.02 * scale_pot)
     worst = [0.0, 0.0]
     for k, (e_pot, e_kin) in zip(steps[1:], ref[1:]):
         g_pot, g_kin = scal[k - 1]
