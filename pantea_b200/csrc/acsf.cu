@@ -579,10 +579,32 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_force_kernel(const AtomArgs<T
             const double* W = tab.weights + tab.w_off[l];
             const double* B = W + (size_t)ni * no;
             const int act = tab.acts[l];
+            // narrow layers (RuNNer: 5 ... 8 neurons): all outputs accumulate together -- `no` independent chains of length
+            // `ni` with the layer's weight rows read as consecutive words, instead of one chain of ni x no dependent
+            // loads and adds; same summation order per neuron (i ascending, then the bias)
+            constexpr int NW = 8;
+            T zz[NW];
+            const bool narrow = no <= NW;
+            if (narrow) {
+#pragma unroll
+                for (int o = 0; o < NW; ++o) zz[o] = (T)0;
+                for (int i = 0; i < ni; ++i) {
+                    const T hi = sh[(in_off + i) * kMlpThreads];
+#pragma unroll
+                    for (int o = 0; o < NW; ++o) if (o < no) zz[o] += hi * (T)W[(size_t)i * no + o];
+                }
+#pragma unroll
+                for (int o = 0; o < NW; ++o) if (o < no) zz[o] += (T)B[o];
+            }
             for (int o = 0; o < no; ++o) {
                 T z = (T)0;
-                for (int i = 0; i < ni; ++i) z += sh[(in_off + i) * kMlpThreads] * (T)W[(size_t)i * no + o];
-                z += (T)B[o];
+                if (narrow) {
+#pragma unroll
+                    for (int q = 0; q < NW; ++q) if (q == o) z = zz[q];
+                } else {
+                    for (int i = 0; i < ni; ++i) z += sh[(in_off + i) * kMlpThreads] * (T)W[(size_t)i * no + o];
+                    z += (T)B[o];
+                }
                 T y, dy;
                 if (act == PANTEA_ACT_TANH) {
                     // inline tanh(z) = sign(z) (1 - 2 / (exp(2|z|) + 1)): the library routine is ~150 instructions of a
@@ -606,10 +628,23 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_force_kernel(const AtomArgs<T
                 const int ni = tab.sizes[l], no = tab.sizes[l + 1];
                 const double* W = tab.weights + tab.w_off[l];
                 const T* da = sdact + (size_t)(lay_out - n_sf) * kMlpThreads;
-                for (int i = 0; i < ni; ++i) {
-                    T acc = (T)0;
-                    for (int o = 0; o < no; ++o) acc += (T)W[(size_t)i * no + o] * (gc[o * kMlpThreads] * da[o * kMlpThreads]);
-                    gn[i * kMlpThreads] = acc;
+                if (no <= 8) {  // the products gc * da once, then one short chain per input, four inputs in flight
+                    T t[8];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) t[o] = o < no ? gc[o * kMlpThreads] * da[o * kMlpThreads] : (T)0;
+#pragma unroll 4
+                    for (int i = 0; i < ni; ++i) {
+                        T acc = (T)0;
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) if (o < no) acc += (T)W[(size_t)i * no + o] * t[o];
+                        gn[i * kMlpThreads] = acc;
+                    }
+                } else {
+                    for (int i = 0; i < ni; ++i) {
+                        T acc = (T)0;
+                        for (int o = 0; o < no; ++o) acc += (T)W[(size_t)i * no + o] * (gc[o * kMlpThreads] * da[o * kMlpThreads]);
+                        gn[i * kMlpThreads] = acc;
+                    }
                 }
                 T* tmp = gc; gc = gn; gn = tmp;
                 lay_out -= ni;

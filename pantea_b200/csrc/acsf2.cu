@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2_MINBLOCKS) hdnnp
     __shared__ int s_next;
     if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
-    constexpr int per_block = kEvalWarps * kAtomsPerWarp;
+    const int per_block = kEvalWarps * a.apw;
     for (int k = next_item(&s_next, lane); k < per_block; k = next_item(&s_next, lane))
         eval2_atom(a, blockIdx.x * per_block + k, lane, wib, smem_raw, s_etab, s_stage[wib]);
 }
@@ -935,7 +935,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2F_MINBLOCKS) hdnn
     __shared__ int s_next;
     if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
-    constexpr int per_block = kEvalWarps * kAtomsPerWarp;
+    const int per_block = kEvalWarps * a.apw;
     for (int k = next_item(&s_next, lane); k < per_block; k = next_item(&s_next, lane))
         eval2f_atom(a, blockIdx.x * per_block + k, lane, wib, smem_raw, s_stage[wib]);
 }
@@ -946,7 +946,17 @@ __global__ void __launch_bounds__(kEvalWarps * 32, PANTEA_EVAL2F_MINBLOCKS) hdnn
 static int g_time_eval = 0;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 
-int launch_v2(const AtomArgs<double>& a, cudaStream_t st) {
+int launch_v2(const AtomArgs<double>& a_in, cudaStream_t st) {
+    AtomArgs<double> a = a_in;
+    {   // atoms per warp: up to kAtomsPerWarp, but never fewer than ~6 resident-block waves of blocks on the device
+        // (a rank that owns 10^4 atoms keeps one atom per warp: the tail of a coarse grid costs more than the idle slots)
+        int dev = 0, sms = 148;
+        PANTEA_CUDA_TRY(cudaGetDevice(&dev));
+        PANTEA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int64_t blocks_min = (int64_t)sms * 4 * 6;
+        int apw = (int)(a.n_work / (kEvalWarps * blocks_min));
+        a.apw = apw < 1 ? 1 : (apw > kAtomsPerWarp ? kAtomsPerWarp : apw);
+    }
     static size_t conf_filter[64] = {0}, conf_eval[64] = {0};
     if (a.max_groups > 0) {
         const size_t smem = (size_t)kFilter2Warps * ((a.scap + 32) * sizeof(float4) + kStrip2 * sizeof(int32_t));
@@ -962,7 +972,7 @@ int launch_v2(const AtomArgs<double>& a, cudaStream_t st) {
     int rc = single ? opt_in_smem((const void*)hdnnp_eval2f_kernel, smem, conf_evalf, "evaluation: neighbour capacity too large for shared memory")
                     : opt_in_smem((const void*)hdnnp_eval2_kernel, smem, conf_eval, "evaluation: neighbour capacity too large for shared memory");
     if (rc != PANTEA_OK) return rc;
-    const int blocks = (a.n_work + kEvalWarps * kAtomsPerWarp - 1) / (kEvalWarps * kAtomsPerWarp);
+    const int blocks = (a.n_work + kEvalWarps * a.apw - 1) / (kEvalWarps * a.apw);
     if (g_time_eval) {  // measurement hook (pantea_eval_timing): CUDA events around the dominant kernel, not capturable
         if (!g_ev0) { PANTEA_CUDA_TRY(cudaEventCreate(&g_ev0)); PANTEA_CUDA_TRY(cudaEventCreate(&g_ev1)); }
         PANTEA_CUDA_TRY(cudaEventRecord(g_ev0, st));

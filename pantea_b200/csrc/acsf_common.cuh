@@ -46,6 +46,7 @@ struct AtomArgs {
     double rc_list;  // radius the neighbour rows were built with (cutoff + Verlet skin)
     float skin;      // Verlet skin: the pair lists must stay valid while atoms move by up to skin / 2 each
     const int32_t* filter_guard;  // skin: the filter is skipped while *filter_guard == 0 (NULL: always run)
+    int apw;                  // fast path: atoms per warp of an evaluation block (drawn from a shared counter)
     int rec_bytes;            // fast path: bytes per staged neighbour record (80: double evaluation, 48: single)
     const int32_t* dup_flag;  // != 0 when two present atoms may coincide (cell-list binning): the pair filters then test exactly
     int dup_always;           // all-pairs mode has no such flag: always test

@@ -13,9 +13,9 @@
 //      straight into the mailbox row of that atom on every rank whose brick + r_cutoff shell contains it -- plain
 //      st.global on peer pointers mapped with CUDA IPC, i.e. NVLink / NVSwitch writes issued by the integration kernel
 //      itself; only halo atoms cross a link.  An atom that leaves the brick also takes its velocity and force rows to
-//      the new owner.  The last block to finish publishes the step number in every peer's flag row
-//      (system-scope release).
-//   2. wait + unpack (ONE kernel).  Blocks wait (bounded spin, system-scope acquire) until every peer has published
+//      the new owner.
+//   2. wait + unpack (ONE kernel).  Its first thread publishes the step number in every peer's flag row (system-scope
+//      release: the integration kernel has completed, its peer stores are performed).  Blocks then wait (bounded spin, system-scope acquire) until every peer has published
 //      this step, then turn the stamped mailbox rows into the dense position array and the roles of this step; rows
 //      with an older stamp are atoms that are not in this rank's shell any more.
 //   3. the unchanged single-GPU pipeline on the present atoms: binning into the GLOBAL cell grid (so rows, and hence
@@ -106,8 +106,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 template <typename T>
 __global__ void mgpu_integrate_push_kernel(int n, const uint8_t* __restrict__ role, const T* __restrict__ pos,
                                            const BrickTable* __restrict__ bt_p, const PeerTable* __restrict__ pt_p,
-                                           const unsigned long long* __restrict__ epoch_p, T dt,
-                                           unsigned int* __restrict__ done) {
+                                           const unsigned long long* __restrict__ epoch_p, T dt) {
     const BrickTable& bt = *bt_p;
     const PeerTable& pt = *pt_p;
     const unsigned long long next = *epoch_p + 1;
@@ -120,7 +119,6 @@ __global__ void mgpu_integrate_push_kernel(int n, const uint8_t* __restrict__ ro
         for (int d = 0; d < 3; ++d) { s_lo[r][d] = bt.edges[d][c[d]]; s_hi[r][d] = bt.edges[d][c[d] + 1]; }
     }
     __syncthreads();
-    int wrote_remote = 0;
     if (id < n && role[id] == 2) {
         const T* vel = (const T*)pt.vel[bt.rank];
         const T* frc = (const T*)pt.frc[bt.rank];
@@ -142,26 +140,12 @@ __global__ void mgpu_integrate_push_kernel(int n, const uint8_t* __restrict__ ro
                 if (bt.dims[d] > 1 && axis_gap((double)x[d], s_lo[r][d], s_hi[r][d], bt.box[d]) > bt.reach) inside = false;
             if (!inside) continue;
             ((MailRec<T>*)pt.mail[r])[(size_t)(next & 1) * n + id] = m;  // NVLink store when r is a peer
-            wrote_remote |= r != bt.rank;
             if (r == owner && r != bt.rank) {  // the atom changes its owner: velocity and force rows travel with it
                 T* pv = (T*)pt.vel[r];
                 T* pf = (T*)pt.frc[r];
 #pragma unroll
                 for (int d = 0; d < 3; ++d) { pv[3 * id + d] = v[d]; pf[3 * id + d] = f[d]; }
             }
-        }
-    }
-    // publish: the block's stores are ordered before its ticket (barrier, then one cumulative system-scope fence), the
-    // last block raises the flags
-    const int any_remote = __syncthreads_or(wrote_remote);
-    if (threadIdx.x == 0) {
-        if (any_remote) __threadfence_system();  // (a block without peer stores has nothing to order across the links)
-        else __threadfence();
-        const unsigned int t = atomicAdd(done, 1u);
-        if (t == gridDim.x - 1) {
-            *done = 0;
-            __threadfence_system();
-            for (int r = 0; r < bt.world; ++r) st_release_sys(pt.flags[r] + bt.rank, next);
         }
     }
 }
@@ -171,14 +155,24 @@ template <typename T>
 __global__ void mgpu_wait_unpack_kernel(int n, uint8_t* __restrict__ role, T* __restrict__ pos,
                                         const BrickTable* __restrict__ bt_p, const PeerTable* __restrict__ pt_p,
                                         const unsigned long long* __restrict__ epoch_p, int advance,
-                                        long long spin_limit, int* __restrict__ err) {
+                                        long long spin_limit, int* __restrict__ err, unsigned int* __restrict__ done) {
     const BrickTable& bt = *bt_p;
     const PeerTable& pt = *pt_p;
     const unsigned long long want = *epoch_p + (advance ? 1 : 0);
+    // publish: the integrate + push kernel before this one has completed (stream order), so its stores -- also those to
+    // peer memory -- are performed; one thread makes that a system-scope release of this rank's step number
+    // (the first block to RUN does it, whichever it is: the blocks that wait below must not be able to keep it off the SMs)
     if (threadIdx.x == 0 && advance) {
+        const unsigned int ticket = atomicAdd(done, 1u);
+        if (ticket == 0) {
+            __threadfence_system();
+            for (int r = 0; r < bt.world; ++r) st_release_sys(pt.flags[r] + bt.rank, want);
+        }
+        if (ticket == gridDim.x - 1) *done = 0;
         const unsigned long long* flags = pt.flags[bt.rank];
         const long long t0 = clock64();
         for (int r = 0; r < bt.world; ++r) {
+            if (r == bt.rank) continue;  // own rows are local and complete (stream order)
             while (ld_acquire_sys(flags + r) < want) {
                 if (clock64() - t0 > spin_limit) { atomicExch(err, 1 + r); break; }  // a peer never arrived: give up, report
                 __nanosleep(200);
@@ -287,10 +281,10 @@ template <typename T>
 int mgpu_step_typed(pantea_mgpu* mg, cudaStream_t st) {
     const int n = (int)mg->n, threads = 256, blocks = (n + threads - 1) / threads;
     mgpu_integrate_push_kernel<T><<<(n + 511) / 512, 512, 0, st>>>(n, mg->role, (const T*)mg->pos, mg->bt_dev, mg->pt_dev, mg->epoch,
-                                                              (T)mg->dt, mg->done);
+                                                              (T)mg->dt);
     PANTEA_LAUNCH_CHECK();
     mgpu_wait_unpack_kernel<T><<<blocks, threads, 0, st>>>(n, mg->role, (T*)mg->pos, mg->bt_dev, mg->pt_dev, mg->epoch, 1,
-                                                           (long long)2e10, mg->err);
+                                                           (long long)2e10, mg->err, mg->done);
     PANTEA_LAUNCH_CHECK();
     int rc = neighbor_build_impl(mg->ws, mg->pos, mg->types, mg->n, mg->bt_host.box, nullptr, nullptr, 1, mg->rc, st);
     if (rc) return rc;
@@ -413,11 +407,11 @@ int pantea_mgpu_set_state(pantea_mgpu* mg, const void* positions, const void* ve
     if (mg->dtype == PANTEA_F64) {
         mgpu_fill_mail_kernel<double><<<blocks, threads, 0, st>>>(n, (const double*)positions, (const double*)velocities, mg->bt_dev, mg->pt_dev, mg->epoch);
         PANTEA_LAUNCH_CHECK();
-        mgpu_wait_unpack_kernel<double><<<blocks, threads, 0, st>>>(n, mg->role, (double*)mg->pos, mg->bt_dev, mg->pt_dev, mg->epoch, 0, 0, mg->err);
+        mgpu_wait_unpack_kernel<double><<<blocks, threads, 0, st>>>(n, mg->role, (double*)mg->pos, mg->bt_dev, mg->pt_dev, mg->epoch, 0, 0, mg->err, mg->done);
     } else {
         mgpu_fill_mail_kernel<float><<<blocks, threads, 0, st>>>(n, (const float*)positions, (const float*)velocities, mg->bt_dev, mg->pt_dev, mg->epoch);
         PANTEA_LAUNCH_CHECK();
-        mgpu_wait_unpack_kernel<float><<<blocks, threads, 0, st>>>(n, mg->role, (float*)mg->pos, mg->bt_dev, mg->pt_dev, mg->epoch, 0, 0, mg->err);
+        mgpu_wait_unpack_kernel<float><<<blocks, threads, 0, st>>>(n, mg->role, (float*)mg->pos, mg->bt_dev, mg->pt_dev, mg->epoch, 0, 0, mg->err, mg->done);
     }
     PANTEA_LAUNCH_CHECK();
     rc = neighbor_build_impl(mg->ws, mg->pos, mg->types, mg->n, mg->bt_host.box, nullptr, nullptr, 1, mg->rc, st);
