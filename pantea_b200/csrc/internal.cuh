@@ -203,6 +203,7 @@ struct pantea_workspace {
     int32_t* owned_slots = nullptr; // [max_atoms] cell-ordered slots of the owned atoms, ascending
     bool owned_active = false;     // rows / evaluation run over `owned_slots` (cell mode with a proper owned range)
     int64_t cell_cap = 0;
+    bool scratch_clean = false;    // cell_fill / cell_own_cnt are all zero (left so by every completed build)
     int32_t* flags = nullptr;      // [4]: max neighbour count seen, ...
     double* e_partial = nullptr;   // reduction scratch
     int64_t e_partial_cap = 0;

@@ -835,11 +835,18 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
         int rcode = ensure_cell_capacity(ws, ncells);
         if (rcode != PANTEA_OK) return rcode;
         ws->mode = kModeCell;
+        const bool was_clean = ws->scratch_clean;
         if (!guard || forced) {  // device-decided rebuilds find the scratch zeroed by the previous rebuild's kernels
-            PANTEA_CUDA_TRY(cudaMemsetAsync(ws->cell_fill, 0, 4 * (ncells + 1), st));
-            if (owned) PANTEA_CUDA_TRY(cudaMemsetAsync(ws->cell_own_cnt, 0, 4 * (ncells + 1), st));
+            // every completed build leaves the counting-sort scratch zeroed (cell_sort_pack / the scan do it), so only
+            // the first build after an allocation -- or after a build that failed half-way -- has to clear it
+            if (!ws->scratch_clean) {
+                PANTEA_CUDA_TRY(cudaMemsetAsync(ws->cell_fill, 0, 4 * (ws->cell_cap + 1), st));
+                PANTEA_CUDA_TRY(cudaMemsetAsync(ws->cell_own_cnt, 0, 4 * (ws->cell_cap + 1), st));
+            }
             PANTEA_CUDA_TRY(cudaMemsetAsync(ws->wide_flag, 0, 8, st));
         }
+        (void)was_clean;
+        ws->scratch_clean = false;  // until this build's kernels are all queued
         cell_assign_kernel<T><<<blocks_n, threads, 0, st>>>(pos, (int)n, ca, ba, ws->cell_of, ws->cell_fill, ws->wide_flag, guard, role,
                                                             owned ? ws->cell_own_cnt : nullptr, own_lo, own_hi);
         PANTEA_LAUNCH_CHECK();
@@ -899,6 +906,7 @@ static int build_typed(pantea_workspace* ws, const void* pos_v, const int32_t* t
     else
         neighbor_rows_kernel<T, kModeAllPairs><<<blocks_w, kWarpsPerBlock * 32, smem, st>>>(rec, ra);
     PANTEA_LAUNCH_CHECK();
+    if (use_cells) ws->scratch_clean = true;
     if (use_skin) {
         skin_refresh_kernel<T><<<blocks_n, threads, 0, st>>>(pos, rec, (int)n);
         PANTEA_LAUNCH_CHECK();

@@ -325,6 +325,7 @@ int ensure_cell_capacity(pantea_workspace* ws, int64_t ncells) {
     PANTEA_CUDA_TRY(cudaMalloc((void**)&ws->cell_own_cnt, 4 * (ncells + 1)));
     PANTEA_CUDA_TRY(cudaMemset(ws->cell_own_cnt, 0, 4 * (ncells + 1)));
     ws->cell_cap = ncells;
+    ws->scratch_clean = false;
     ws->skin_active = false;  // fresh (unzeroed) binning scratch: the next build is a forced one
     ++ws->arg_epoch;
     return PANTEA_OK;
