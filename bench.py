@@ -229,7 +229,9 @@ def run_preprocess(pot, rank, world, dev, n_structs=10000, atoms=192, batch=1250
                 kept.append(res)
         return params, kept
 
-    process()  # warm-up: capacities, lazy allocations
+    warm, _ = process()  # warm-up: capacities, lazy allocations ...
+    for el in ("H", "O"):
+        merge_scaler_params(warm[el])  # ... and the collectives' first-use set-up
     torch.cuda.synchronize()
     if world > 1:
         import torch.distributed as dist
