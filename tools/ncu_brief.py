@@ -1,8 +1,11 @@
-"""Short per-kernel digest of an .ncu-rep: python tools/ncu_brief.py rep"""
+"""Short per-kernel digest of an .ncu-rep: python tools/ncu_brief.py rep [--cols 0,1]  (launch indices to keep)"""
 import csv, subprocess, sys
 raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[0]
+if '--cols' in sys.argv:
+    keep = [int(c) for c in sys.argv[sys.argv.index('--cols') + 1].split(',')]
+    rows = rows[:2] + [rows[2 + c] for c in keep]
 want = ['Kernel Name', 'gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__occupancy_limit_registers',
         'launch__occupancy_limit_shared_mem', 'launch__shared_mem_per_block_dynamic', 'launch__shared_mem_per_block_static',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
