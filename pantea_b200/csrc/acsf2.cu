@@ -31,7 +31,10 @@ constexpr int kTab2 = 256;                // entries of the 2^(i/256) table
 #define PANTEA_CHUNK2 8
 #endif
 constexpr int kChunk2 = PANTEA_CHUNK2;    // pair-list iterations per cp.async group (4 or 8)
-constexpr int kFilter2Warps = 8;
+#ifndef PANTEA_FILTER2_WARPS
+#define PANTEA_FILTER2_WARPS 4  // with 7 blocks per SM (72 registers): 28 warps; 8 x 3 at 80 registers measured 6 % slower
+#endif
+constexpr int kFilter2Warps = PANTEA_FILTER2_WARPS;
 
 // Atoms per block of the evaluation / filter kernels: the warps of a block draw the block's atoms from a shared counter
 // one after the other.  With one atom per warp the block lives as long as its most expensive atom (an O centre walks
@@ -127,27 +130,107 @@ __device__ __forceinline__ D2 lds128(const unsigned char* p) { return *reinterpr
 #endif
 constexpr int kStrip2 = 1024 + 128;  // entries of a warp's emission strip: one full tile behind an unflushed remainder
 
+// The pair test runs on the tensor cores.  For a resident neighbour l and a swept neighbour s (vectors from the centre)
+//     (|s - l|^2 - thr) / 2  =  -l.s + |s|^2 / 2 + (|l|^2 / 2 - thr / 2)
+// is one row-times-column product of a 16 x 8 x 8 TF32 tile: row l of A = (-x, -y, -z, 1, L1, L2, 0, 0) with the row
+// constants L1 = |l|^2 / 2 - thr / 2 (cutoff test) and L2 = |l|^2 - r2max / 2 (Gaussian screening); column s of B =
+// (x, y, z, |s|^2 / 2, 1, 0, 0, 0) for the cutoff test and (x, y, z, |s|^2, 0, 1, 0, 0) for the screening test.  A pair is
+// kept when the result is negative (sign bit).  The staged vectors are rounded to TF32 first, so the products are exact in
+// the FP32 accumulator and the test is the exact distance of the ROUNDED points (each moved by at most 2^-11 of its
+// length) plus the TF32 rounding / truncation of the three constants: the threshold is inflated by 5e-3 of the squared list
+// radius to cover both.  The lists are inclusive anyway (the evaluation's cutoff function makes the final cut); the margin adds
+// ~0.7 % zero-weight entries.  One instruction replaces 128 x 9 scalar ones.
+__device__ __forceinline__ float to_tf32(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const float (&a)[4], float b0, float b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+          "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)), "f"(0.f));
+}
+// Survivor masks of a 32 x 32 tile follow the accumulator layout: lane (g = lane / 4, t = lane % 4) holds, for column
+// block c (8 swept neighbours) and row block h (16 residents), elements j = 2 u + p at tile row 16 h + 8 u + g and tile
+// column 2 t + p of the block.  Bit 31 - (8 c + 4 h + j) of the lane's mask is that element, i.e. byte 3 - c belongs to
+// column block c.  Which neighbour sits in a tile row / column is free: row (h, u, g) is resident 4 g + 2 h + u and column
+// n of block c is swept neighbour 8 c + (n + 2 c) % 8, so that the entries a lane emits combine 4 consecutive residents
+// with 8 swept neighbours of distinct index modulo 8 -- the evaluation's 16-byte record reads of consecutive entries then
+// fall into different shared-memory banks (records 8 apart share their banks).
+__host__ __device__ constexpr int tile_row(int g, int h, int u) { return 4 * g + 2 * h + u; }
+__host__ __device__ constexpr int tile_col(int t, int c, int p) { return 8 * c + ((2 * t + p + 2 * c) & 7); }
+struct TriMaskTable {
+    unsigned m[32];
+    constexpr TriMaskTable() : m() {
+        for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, t = lane & 3;
+            unsigned v = 0;
+            for (int c = 0; c < 4; ++c)
+                for (int h = 0; h < 2; ++h)
+                    for (int j = 0; j < 4; ++j)
+                        if (tile_col(t, c, j & 1) < tile_row(g, h, j >> 1)) v |= 1u << (31 - (8 * c + 4 * h + j));
+            m[lane] = v;
+        }
+    }
+};
+__constant__ const TriMaskTable kTriMask2 = TriMaskTable();
+// rows below n (indexed [n][g]) / columns below n (indexed [n][t]) of a tile, n = 0 .. 32
+struct RowMaskTable {
+    unsigned m[33][8];
+    constexpr RowMaskTable() : m() {
+        for (int n = 0; n <= 32; ++n)
+            for (int g = 0; g < 8; ++g) {
+                unsigned v = 0;
+                for (int c = 0; c < 4; ++c)
+                    for (int h = 0; h < 2; ++h)
+                        for (int j = 0; j < 4; ++j)
+                            if (tile_row(g, h, j >> 1) < n) v |= 1u << (31 - (8 * c + 4 * h + j));
+                m[n][g] = v;
+            }
+    }
+};
+struct ColMaskTable {
+    unsigned m[33][4];
+    constexpr ColMaskTable() : m() {
+        for (int n = 0; n <= 32; ++n)
+            for (int t = 0; t < 4; ++t) {
+                unsigned v = 0;
+                for (int c = 0; c < 4; ++c)
+                    for (int h = 0; h < 2; ++h)
+                        for (int j = 0; j < 4; ++j)
+                            if (tile_col(t, c, j & 1) < n) v |= 1u << (31 - (8 * c + 4 * h + j));
+                m[n][t] = v;
+            }
+    }
+};
+__constant__ const RowMaskTable kRowMask2 = RowMaskTable();
+__constant__ const ColMaskTable kColMask2 = ColMaskTable();  // swept index below the resident one (lower triangle of a chunk's own tile)
+
 // State of one warp's walk over the angular groups of its atom.
 struct Filter2 {
-    const float4* sf4;   // staged (dx, dy, dz, r^2) of the neighbours
+    const float4* sf4;   // staged TF32-rounded (dx, dy, dz, r^2 / 2) of the neighbours
     int32_t* list;       // the atom's pair list in global memory
     int32_t* strip;      // the warp's shared-memory emission strip
     int pair_cap, off, fill, lane;
-    int rb;  // bytes per staged neighbour record of the evaluation that will walk the list (80: double, 48: single)
-    float rc2f;
-    // exact coincidence test (only when the binning saw atoms at the same position): staged index -> exact difference
-    const void* rec;     // Rec<T>[]
-    const int32_t* row;  // the centre's neighbour row
-    int slot;
-    double blx, bly, blz;
-    bool pbc, exact;
-    float r2max;  // Gaussian screening: pairs with r_j^2 + r_k^2 + r_jk^2 above it are dropped (huge: no screening)
-    bool cls_test, screen;
+    int rb;      // bytes per staged neighbour record of the evaluation that will walk the list (80: double, 48: single)
+    float thr1;  // inclusive squared cutoff of r_jk (margins: see above)
+    float r2max;  // Gaussian screening: pairs with r_j^2 + r_k^2 + r_jk^2 above it are dropped (unused without screening)
+    bool cls_test, screen, exact;
+    int slot;  // exact coincidence test (only when the binning saw atoms at the same position)
 
-    // compacts `mask` (bit b <-> entry e0 + b * stride; DIAG: minus wrap_sub from bit wrap_b on) into the strip, then
-    // flushes the strip's full 128-entry blocks with one 16-byte store per lane
-    template <bool DIAG>
-    __device__ __forceinline__ void emit(unsigned mask, int nb, int e0, int stride, int wrap_b, int wrap_sub) {
+    // the 8 bits of one column block (MSB first: rows 2 h + u = 0 .. 3, two columns each) -> entries at q
+    __device__ __forceinline__ void emit_block(int32_t*& q, unsigned m8, const int (&rpart)[4], int e0, int e1) const {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (m8 & (0x80u >> k)) { *q = rpart[k >> 1] + ((k & 1) ? e1 : e0); ++q; }
+    }
+
+    // compacts `mask` (tile layout above; rpart[2 h + u]: entry part of the lane's four rows, cb0 + tile_col * stride:
+    // entry part of its columns) into the strip, lane by lane, then flushes the strip's full 128-entry blocks with one
+    // 16-byte store per lane
+    __device__ __forceinline__ void emit(unsigned mask, int ncb, const int (&rpart)[4], int cb0, int stride) {
+        const int t2 = 2 * (lane & 3);
         const int c = __popc(mask);
         int incl = c;
 #pragma unroll
@@ -157,14 +240,20 @@ struct Filter2 {
         }
         const int total = __shfl_sync(kFullMask, incl, 31);
         int32_t* q = strip + fill + (incl - c);
-        for (int b0 = 0; b0 < nb; b0 += 8) {
-            const unsigned m8 = mask >> b0;
-            int e = e0 + b0 * stride;
-            if (DIAG && b0 > wrap_b) e -= wrap_sub;
-#pragma unroll
-            for (int b = 0; b < 8; ++b, e += stride) {
-                if (DIAG && b0 + b == wrap_b) e -= wrap_sub;
-                if (m8 & (1u << b)) *q++ = e;
+        if (ncb == 4) {  // full tile: the four column blocks are independent store chains
+            int32_t* q1 = q + __popc(mask >> 24);
+            int32_t* q2 = q + __popc(mask >> 16);
+            int32_t* q3 = q + __popc(mask >> 8);
+            const int e0 = cb0 + t2 * stride, e1 = cb0 + (8 + ((t2 + 2) & 7)) * stride;
+            const int e2 = cb0 + (16 + ((t2 + 4) & 7)) * stride, e3 = cb0 + (24 + ((t2 + 6) & 7)) * stride;
+            emit_block(q, mask >> 24, rpart, e0, e0 + stride);
+            emit_block(q1, mask >> 16, rpart, e1, e1 + stride);
+            emit_block(q2, mask >> 8, rpart, e2, e2 + stride);
+            emit_block(q3, mask, rpart, e3, e3 + stride);
+        } else {
+            for (int cb = 0; cb < ncb; ++cb) {
+                const int e0 = cb0 + (8 * cb + ((t2 + 2 * cb) & 7)) * stride;
+                emit_block(q, mask >> (24 - 8 * cb), rpart, e0, e0 + stride);
             }
         }
         fill += total;
@@ -199,18 +288,16 @@ struct Filter2 {
         return padn;
     }
 
-    // resident chunk (lanes hold staged neighbours r0 + lane, lane < nres; their record offset goes into the entry half
-    // selected by res_shift) against the swept range [s_begin, s_begin + ns): tiles of 32 broadcast reads
-    // tri: resident chunk and swept range are the same neighbours -- only the pairs with the swept index below the
-    // resident one are kept (lower triangle of the tile)
     // true when staged neighbours n1 and n2 sit at exactly the same position as seen from the centre (d_ij == d_ik in
     // every component: the reference's r_jk is then 0 and it drops the triplet, acsf.py:316-325)
     template <typename T>
-    __device__ __forceinline__ bool coincident(int n1, int n2) const {
-        const Rec<T>* rc_ = (const Rec<T>*)rec;
-        const T lx = (T)blx, ly = (T)bly, lz = (T)blz;
-        const Rec<T> ri = rc_[slot];
-        const Rec<T> r1 = rc_[row[n1]], r2 = rc_[row[n2]];
+    __device__ __forceinline__ bool coincident(const AtomArgs<T>& a, int n1, int n2) const {
+        T lx, ly, lz;
+        bool pbc;
+        item_box(a, slot, lx, ly, lz, pbc);
+        const int32_t* row = a.nbr + (size_t)slot * a.cap;
+        const Rec<T> ri = a.rec[slot];
+        const Rec<T> r1 = a.rec[row[n1]], r2 = a.rec[row[n2]];
         T d1[3] = {sub_rn(ri.x, r1.x), sub_rn(ri.y, r1.y), sub_rn(ri.z, r1.z)};
         T d2[3] = {sub_rn(ri.x, r2.x), sub_rn(ri.y, r2.y), sub_rn(ri.z, r2.z)};
         if (pbc) {
@@ -220,75 +307,121 @@ struct Filter2 {
         return d1[0] == d2[0] && d1[1] == d2[1] && d1[2] == d2[2];
     }
 
-    template <typename T>
-    __device__ __forceinline__ void rect(int r0, int nres, int res_shift, int s_begin, int ns, bool tri = false) {
-        const float4 fl = sf4[r0 + (lane < nres ? lane : 0)];
-        const bool l_ok = lane < nres && (!cls_test || fl.w < rc2f);
-        const int res_part = ((r0 + lane) * rb) << res_shift;
-        const int stride = rb << (16 - res_shift);
-        const float al = r2max - fl.w;  // screening: r_jk^2 must stay below al - r_s^2
-        for (int s0 = 0; s0 < ns; s0 += 32) {
-            const int nb = min(32, ns - s0);
-            unsigned mask = 0;
-            const float4* p = sf4 + s_begin + s0;
-            for (int b0 = 0; b0 < nb; b0 += 8, p += 8) {  // blocks of eight steps with compile-time bit positions; a
-                unsigned m8 = 0;                           // partial block reads past the range (inside the staging array)
+    // one column block: 8 swept neighbours against the lane's 32 resident rows; returns the 8 sign bits (MSB first)
+    template <bool SCREEN>
+    __device__ __forceinline__ unsigned column_block(float bv, float bmul, float k4, float k5, const float (&ra)[2][4]) const {
+        unsigned mask = 0;
+        float d[2][4];
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const float4 fs = p[b];  // warp-uniform address: broadcast
-                    const float ex = fs.x - fl.x, ey = fs.y - fl.y, ez = fs.z - fl.z;
-                    const float d2 = ex * ex + ey * ey + ez * ez;
-                    const float thr = screen ? fminf(rc2f, al - fs.w) : rc2f;
-                    if (d2 < thr) m8 |= 1u << b;
-                }
-                mask |= m8 << b0;
+        for (int h = 0; h < 2; ++h) mma_tf32_16x8x8(d[h], ra[h], bv, k4);
+        if (SCREEN) {  // second test: (r_jk^2 + r_s^2 + r_l^2 - r2max) / 2
+            const float bv2 = bv * bmul;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float e[4];
+                mma_tf32_16x8x8(e, ra[h], bv2, k5);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[h][j] = fmaxf(d[h][j], e[j]);
             }
-            if (nb < 32) mask &= (1u << nb) - 1u;
-            if (cls_test) mask &= __ballot_sync(kFullMask, lane < nb && sf4[s_begin + s0 + lane].w < rc2f);
-            if (!l_ok) mask = 0;
-            if (tri) mask &= (1u << lane) - 1u;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mask = __funnelshift_l(__float_as_uint(d[h][j]), mask, 1);
+        return mask;
+    }
+
+    // resident chunk (staged neighbours r0 .. r0 + nres - 1, nres <= 32; their record offset goes into the entry half
+    // selected by res_shift) against the swept range [s_begin, s_begin + ns): tiles of 32 x 32 pair tests on the tensor cores
+    // tri: resident chunk and swept range are the same neighbours -- only the pairs with the swept index below the
+    // resident one are kept (lower triangle of the tile)
+    template <typename T>
+    __device__ __forceinline__ void rect(const AtomArgs<T>& a, int r0, int nres, int res_shift, int s_begin, int ns, bool tri) {
+        const float* sf = reinterpret_cast<const float*>(sf4);
+        const int g = lane >> 2, t = lane & 3;
+        float ra[2][4];
+        int rpart[4];
+        const float h1 = 0.5f * thr1, h2 = 0.5f * r2max;
+        const float* pr = sf + (r0 + 4 * g) * 4;  // the lane's four rows: residents r0 + 4 g .. + 3 (rows past nres: masked)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = 2 * h + u;
+                const float v = pr[4 * i + t], sq = pr[4 * i + 3];
+                ra[h][u] = t == 3 ? 1.f : -v;
+                const float l1 = sq - h1, l2 = fmaf(2.f, sq, -h2);  // not rounded: the tensor core drops their low 13 bits (in the margin)
+                ra[h][2 + u] = t == 0 ? l1 : (t == 1 ? l2 : 0.f);
+            }
+        const int rstep = rb << res_shift;
+        rpart[0] = ((r0 + 4 * g) * rb) << res_shift;
+#pragma unroll
+        for (int i = 1; i < 4; ++i) rpart[i] = rpart[i - 1] + rstep;
+        unsigned rowmask = kRowMask2.m[nres][g];
+        if (cls_test) {  // rows reach beyond the cutoff (skin): residents past it do not count
+            unsigned rowbyte = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (2.f * pr[4 * i + 3] < thr1) rowbyte |= 0xC0u >> (2 * i);
+            rowmask &= rowbyte * 0x01010101u;
+        }
+        if (tri) rowmask &= kTriMask2.m[lane];
+        const float bmul = t == 3 ? 2.f : 1.f, k4 = t == 0 ? 1.f : 0.f, k5 = t == 1 ? 1.f : 0.f;
+        const int stride = rb << (16 - res_shift);
+        const float* pb = sf + s_begin * 4 + t;  // a partial tile reads past the range (inside the staging array)
+        for (int s0 = 0; s0 < ns; s0 += 32, pb += 128) {
+            const int nb = min(32, ns - s0);
+            const int ncb = (nb + 7) >> 3;
+            unsigned mask = 0;
+            if (nb == 32) {  // four independent blocks
+                unsigned m4[4];
+                if (screen) {
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb) m4[cb] = column_block<true>(pb[32 * cb + 4 * ((g + 2 * cb) & 7)], bmul, k4, k5, ra);
+                } else {
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb) m4[cb] = column_block<false>(pb[32 * cb + 4 * ((g + 2 * cb) & 7)], bmul, k4, k5, ra);
+                }
+                mask = __byte_perm(__byte_perm(m4[3], m4[2], 0x0040), __byte_perm(m4[1], m4[0], 0x0040), 0x5410);
+            } else {
+#pragma unroll 1
+                for (int cb = 0; cb < ncb; ++cb) {
+                    const float bv = pb[32 * cb + 4 * ((g + 2 * cb) & 7)];
+                    mask = (mask << 8) | (screen ? column_block<true>(bv, bmul, k4, k5, ra) : column_block<false>(bv, bmul, k4, k5, ra));
+                }
+                mask <<= 8 * (4 - ncb);
+            }
+            unsigned valid = rowmask & kColMask2.m[nb][t];
+            if (cls_test) {  // with a skin: swept neighbours past the cutoff do not count
+                unsigned colmask = 0;
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
+                    const int col = tile_col(t, cb, 0);  // the lane's two columns of a block are neighbours col, col + 1
+                    const bool ok0 = 2.f * sf[(s_begin + s0 + col) * 4 + 3] < thr1, ok1 = 2.f * sf[(s_begin + s0 + col + 1) * 4 + 3] < thr1;
+                    colmask |= ((ok0 ? 0xAAu : 0u) | (ok1 ? 0x55u : 0u)) << (24 - 8 * cb);
+                }
+                valid &= colmask;
+            }
+            mask &= valid;
             if (PANTEA_EXACT_ON && exact) {  // rare: drop the pairs of exactly coincident neighbours (candidates: identical staged vectors)
                 unsigned zz = mask;
                 while (zz) {
-                    const int b = __ffs(zz) - 1;
-                    zz &= zz - 1;
-                    const float4 fs = sf4[s_begin + s0 + b];
-                    if (fs.x == fl.x && fs.y == fl.y && fs.z == fl.z && coincident<T>(r0 + lane, s_begin + s0 + b)) mask &= ~(1u << b);
+                    const int bit = 31 - __clz(zz);
+                    zz &= ~(1u << bit);
+                    const int k = 31 - bit;
+                    const int rw = r0 + tile_row(g, (k >> 2) & 1, (k >> 1) & 1);
+                    const int cl = s_begin + s0 + tile_col(t, k >> 3, k & 1);
+                    const float4 fs = sf4[cl], fl = sf4[rw];
+                    if (fs.x == fl.x && fs.y == fl.y && fs.z == fl.z && coincident<T>(a, rw, cl)) mask &= ~(1u << bit);
                 }
             }
-            emit<false>(mask, nb, res_part + (((s_begin + s0) * rb) << (16 - res_shift)), stride, 0, 0);
+            emit(mask, ncb, rpart, ((s_begin + s0) * rb) << (16 - res_shift), stride);
         }
-    }
-
-    // unordered pairs inside [r0, r0 + nres), nres <= 32: lane L meets (L + s) mod nres for s = 1 .. nres / 2 (for even
-    // nres the last step only on the lower half of the lanes), i.e. every pair once with all lanes busy
-    __device__ __forceinline__ void diag(int r0, int nres) {
-        if (nres < 2) return;
-        const bool l_in = lane < nres;
-        const float4 fl = sf4[r0 + (l_in ? lane : 0)];
-        const bool l_ok = l_in && (!cls_test || fl.w < rc2f);
-        const float al = r2max - fl.w;
-        const int h = nres >> 1;
-        unsigned mask = 0;
-        int pidx = lane + 1;  // partner of step s = 1
-        for (int s = 1; s <= h; ++s, ++pidx) {
-            if (pidx >= nres) pidx -= nres;
-            const float4 fs = sf4[r0 + (l_in ? pidx : 0)];
-            const float ex = fs.x - fl.x, ey = fs.y - fl.y, ez = fs.z - fl.z;
-            const float d2 = ex * ex + ey * ey + ez * ez;
-            bool live = d2 < (screen ? fminf(rc2f, al - fs.w) : rc2f) && (!cls_test || fs.w < rc2f);
-            if (s == h && !(nres & 1)) live = live && lane < h;
-            if (live) mask |= 1u << (s - 1);
-        }
-        if (!l_ok) mask = 0;
-        // entry: lane's record in the low half, partner L + 1 + b (minus nres once it wraps) in the high half
-        const int e0 = ((r0 + lane) * rb) | (((r0 + lane + 1) * rb) << 16);
-        emit<true>(mask, h, e0, rb << 16, nres - 1 - lane, (nres * rb) << 16);
     }
 };
 
 #ifndef PANTEA_FILTER2_MINBLOCKS
-#define PANTEA_FILTER2_MINBLOCKS 3
+#define PANTEA_FILTER2_MINBLOCKS 7
 #endif
 template <typename T>
 __device__ __forceinline__ void filter2_atom(const AtomArgs<T>& a, int w, int lane, int wib, unsigned char* smem_raw) {
@@ -312,9 +445,10 @@ __device__ __forceinline__ void filter2_atom(const AtomArgs<T>& a, int w, int la
     bool pbc;
     item_box(a, slot, lx, ly, lz, pbc);
 
-    // stage (dx, dy, dz, r^2): differences formed in T, then rounded to float
+    // stage (dx, dy, dz, r^2 / 2): differences formed in T, then rounded to TF32
     const float rcf = tab.n_cls > 0 ? (float)tab.cls[0].rc + a.skin : 0.f;
     const float rc2f = rcf * rcf * 1.0001f + 1e-4f;  // inclusive: the exact test is the evaluation's
+    const float tf32_margin = 5.0e-3f * (float)(a.rc_list * a.rc_list) + 1e-3f;  // rounded vectors and constants (see mma_tf32_16x8x8)
     {
         const Rec<T> ri = a.rec[slot];
         const int32_t* row = a.nbr + (size_t)slot * a.cap;
@@ -336,9 +470,8 @@ __device__ __forceinline__ void filter2_atom(const AtomArgs<T>& a, int w, int la
                 if (n < sg.total) {
                     T dx = sub_rn(ri.x, rr[r].x), dy = sub_rn(ri.y, rr[r].y), dz = sub_rn(ri.z, rr[r].z);
                     if (pbc) { dx = min_image(dx, lx); dy = min_image(dy, ly); dz = min_image(dz, lz); }
-                    const float fx = (float)dx, fy = (float)dy, fz = (float)dz;
-                    const float r2 = fx * fx + fy * fy + fz * fz;
-                    sf4[n] = make_float4(fx, fy, fz, r2);
+                    const float fx = to_tf32((float)dx), fy = to_tf32((float)dy), fz = to_tf32((float)dz);
+                    sf4[n] = make_float4(fx, fy, fz, to_tf32(0.5f * (fx * fx + fy * fy + fz * fz)));
                 }
             }
         }
@@ -347,9 +480,8 @@ __device__ __forceinline__ void filter2_atom(const AtomArgs<T>& a, int w, int la
 
     Filter2 f;
     f.sf4 = sf4; f.list = a.pairs + (size_t)w * a.pair_cap; f.strip = strip; f.pair_cap = a.pair_cap; f.off = 0; f.fill = 0;
-    f.lane = lane; f.rc2f = rc2f;
-    f.rec = a.rec; f.row = a.nbr + (size_t)slot * a.cap; f.slot = slot; f.blx = (double)lx; f.bly = (double)ly; f.blz = (double)lz;
-    f.pbc = pbc; f.exact = a.dup_flag && *a.dup_flag != 0;
+    f.lane = lane; f.thr1 = rc2f + tf32_margin;
+    f.slot = slot; f.exact = a.dup_flag && *a.dup_flag != 0;
     f.cls_test = tab.n_cls > 0 && tab.cls[0].rc + (double)a.skin < a.rc_list;  // rows reach beyond the cutoff
     f.rb = a.rec_bytes;
     const int pad_entry = (sg.total * f.rb) | ((sg.total * f.rb) << 16);
@@ -375,13 +507,13 @@ __device__ __forceinline__ void filter2_atom(const AtomArgs<T>& a, int w, int la
             if (reach < 3.f * rc2f) {  // otherwise nothing inside the cutoff sphere can be dropped
                 float b1 = 3.0e38f, b2 = 3.0e38f;  // smallest r^2 of the j bucket / of the k bucket (same type: second smallest)
                 int i1 = -1, i2 = -1;
-                for (int n = lane; n < nj; n += 32) { const float v = sf4[bj + n].w; if (v < b1) { b1 = v; i1 = bj + n; } }
+                for (int n = lane; n < nj; n += 32) { const float v = 2.f * sf4[bj + n].w; if (v < b1) { b1 = v; i1 = bj + n; } }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     const float v = __shfl_xor_sync(kFullMask, b1, o); const int iv = __shfl_xor_sync(kFullMask, i1, o);
                     if (v < b1 || (v == b1 && iv < i1)) { b1 = v; i1 = iv; }
                 }
-                for (int n = lane; n < nk; n += 32) { const float v = sf4[bk + n].w; if (v < b2 && bk + n != i1) { b2 = v; i2 = bk + n; } }
+                for (int n = lane; n < nk; n += 32) { const float v = 2.f * sf4[bk + n].w; if (v < b2 && bk + n != i1) { b2 = v; i2 = bk + n; } }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     const float v = __shfl_xor_sync(kFullMask, b2, o); const int iv = __shfl_xor_sync(kFullMask, i2, o);
@@ -391,7 +523,7 @@ __device__ __forceinline__ void filter2_atom(const AtomArgs<T>& a, int w, int la
                     const float4 p1 = sf4[i1], p2 = sf4[i2];
                     const float ex = p1.x - p2.x, ey = p1.y - p2.y, ez = p1.z - p2.z;
                     const float ref = b1 + b2 + ex * ex + ey * ey + ez * ez;
-                    f.r2max = (ref + reach) * 1.001f + 1e-3f;
+                    f.r2max = (ref + reach) * 1.001f + 2.f * tf32_margin;  // the three squared distances carry TF32 rounding
                     f.screen = true;
                 }
             }
@@ -406,25 +538,26 @@ __device__ __forceinline__ void filter2_atom(const AtomArgs<T>& a, int w, int la
         const int rshift = res_k ? 16 : 0;
         const int full = nr >> 5, rem = nr & 31;
         const int n_tail = rem == 0 ? 0 : (same ? full + 1 : (ns + 31) >> 5);
-        for (int it = 0; it < full + n_tail; ++it) {
+        const int n_items = (full + n_tail) << (same ? 1 : 0);  // same-type groups: odd items are the chunks' own triangles
+        for (int it2 = 0; it2 < n_items; ++it2) {
+            const int it = same ? it2 >> 1 : it2;
             int r0, nres, shift, s_begin, s_len;
-            bool do_diag = false;
-            if (it < full) {  // a full resident chunk: (same-type) everything before it and its own triangle, else everything
-                r0 = rb + 32 * it; nres = 32; shift = rshift; s_begin = sb; s_len = same ? 32 * it : ns; do_diag = same;
-            } else if (same) {  // remainder of the bucket: swept against the full chunks, then its own triangle
+            if (it < full) {  // a full resident chunk: (same-type) everything before it, else everything
+                r0 = rb + 32 * it; nres = 32; shift = rshift; s_begin = sb; s_len = same ? 32 * it : ns;
+            } else if (same) {  // remainder of the bucket: swept against the full chunks
                 const int c = it - full;
                 if (c < full) { r0 = rb + 32 * c; nres = 32; shift = 16; s_begin = rb + 32 * full; s_len = rem; }
-                else { r0 = rb + 32 * full; nres = rem; shift = 16; s_begin = 0; s_len = 0; do_diag = true; }
+                else { r0 = rb + 32 * full; nres = rem; shift = 16; s_begin = 0; s_len = 0; }
             } else {  // remainder of the resident bucket: swept against resident chunks of the other bucket
                 const int q = it - full;
                 r0 = sb + 32 * q; nres = min(32, ns - 32 * q); shift = 16 - rshift; s_begin = rb + 32 * full; s_len = rem;
             }
-            if (s_len > 0) f.template rect<T>(r0, nres, shift, s_begin, s_len);
-#ifdef PANTEA_FILTER2_WRAP_DIAG
-            if (do_diag) f.diag(r0, nres);
-#else
-            if (do_diag && nres > 1) f.template rect<T>(r0, nres, 16, r0, nres, true);  // the chunk's own triangle: a masked tile
-#endif
+            bool tri = false;
+            if (same && (it2 & 1)) {  // the chunk's own triangle: a masked tile
+                const bool own = it < full || it == 2 * full;  // full chunks and the remainder chunk (not the remainder-vs-chunk items)
+                tri = true; shift = 16; s_begin = r0; s_len = (own && nres > 1) ? nres : 0;
+            }
+            if (s_len > 0) f.template rect<T>(a, r0, nres, shift, s_begin, s_len, tri);
         }
         n_real -= f.finish_group(pad_entry);
         n_real += f.off - seg_begin;
