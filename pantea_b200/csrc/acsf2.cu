@@ -105,7 +105,11 @@ __device__ __forceinline__ double exp_tab256(double y, const double* __restrict_
     p = fma(p, f, 0.5);
     p = fma(p, f, 1.0);
     p = fma(p, f, 1.0);
+#ifdef PANTEA_EXP_PROBE
+    p *= tab[n & 15];  // timing probe only (wrong values): conflict-free table reads
+#else
     p *= tab[n & (kTab2 - 1)];
+#endif
     return __hiloint2double(__double2hiint(p) + (n >> 8) * 0x100000, __double2loint(p));
 }
 // max(x, ~0) for finite x through the sign / exponent word: negative values (and -0) come out as a positive number
