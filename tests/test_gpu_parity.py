@@ -610,3 +610,40 @@ def test_fast_path_and_mixed_precision_against_oracle(n_atoms, pot):
     assert rel_err(e_fast[:m].cpu().numpy(), ea_o[:m]) < 1e-10 and rel_err(e_scr[:m].cpu().numpy(), ea_o[:m]) < 1e-10
     assert float((f_scr - f_fast).abs().max()) < 1e-13 * float(f_fast.abs().max())  # what screening drops is below 1e-14 of G
     assert err_over(f_mix, 1e-5) <= 1.0
+
+
+@pytest.mark.parametrize("jitter", [0.0, 1e-9, 1e-4])
+def test_fast_path_pairs_at_the_cutoff_distance(jitter, pot):
+    """Pair lists of the fast path are built from TF32 distance tiles with an inclusive margin (csrc/acsf2.cu): a cubic
+    lattice of spacing r_c / 3 puts thousands of neighbour pairs (j, k) exactly at r_jk = r_c, and 30 neighbours of every
+    atom exactly at r_ij = r_c; a jitter moves them to either side within rounding (1e-9) or within the margin (1e-4).
+    Forces must still match the oracle to 1e-10 (a dropped live pair or a kept dead one shows at 1e-4 and above)."""
+    from pantea_b200 import _lib
+    lib = _lib.load()
+    n, a = 15, 4.0  # 3 375 atoms, box 60 Bohr >= 4 r_c, 122 lattice sites inside r_c = 12
+    g = np.arange(n)
+    ix, iy, iz = np.meshgrid(g, g, g, indexing="ij")
+    pos = np.stack([ix, iy, iz], -1).reshape(-1, 3) * a
+    rng = np.random.default_rng(5)
+    pos = np.remainder(pos + jitter * rng.standard_normal(pos.shape) + 0.5 * a, n * a)
+    t_h, t_o = pot[0].atom_type, pot[1].atom_type
+    types = np.where((ix + iy + iz).reshape(-1) % 3 == 0, t_o, t_h).astype(np.int64)
+    box = np.array([n * a] * 3)
+    dev = device_potential_from_specs(pot)
+    ws = _workspace(dev, len(pos), cap=160)
+    ws.bind(cuda(pos), cuda(types, torch.int32), box, dev.r_cutoff)
+    _, ea_o, f_o = c_oracle.energy_forces(pot, pos, types, box)
+    f_o = torch.as_tensor(f_o, device="cuda")
+    scale = float(f_o.abs().max()) + 1e-30
+    try:
+        lib.pantea_set_fast_path(1)
+        _, e_atom, f = ws.energy_forces(False, True, True)
+        f, e_atom = f.clone(), e_atom.clone()
+        lib.pantea_set_fast_path(0)
+        _, _, f_gen = ws.energy_forces(False, True)
+    finally:
+        lib.pantea_set_fast_path(1)
+    # the jittered lattice has (near-)cancelling forces: the element-wise test uses the per-atom energy as well
+    assert rel_err(e_atom.cpu().numpy(), ea_o) < 1e-10
+    assert float((f - f_o).abs().max()) < 1e-10 * max(scale, 1e-3)
+    assert float((f_gen - f_o).abs().max()) < 1e-10 * max(scale, 1e-3)
