@@ -6,7 +6,6 @@ run() { # world, port, extra args...
   if [ $w = 1 ]; then timeout 600 python "$@"; else timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $w --master-addr 127.0.0.1 --master-port $port "$@"; fi
 }
 run 8 29521 tests/mgpu_check.py 24000 20 brick oracle > $out/check_w8.txt 2>&1; grep "^brick" $out/check_w8.txt | tail -2
-run 4 29522 tests/mgpu_check.py 24000 20 brick oracle > $out/check_w4.txt 2>&1; grep "^brick" $out/check_w4.txt | tail -1
 for w in 8 4 2 1; do
   run $w $((29530 + w)) bench.py --gpus $w --steps 100 --no-cpu-baseline > $out/bench_n$w.json 2> $out/bench_n$w.err
   python - <<PY
@@ -18,12 +17,3 @@ except Exception as e: print('N=$w failed', e)
 PY
 done
 run 8 29541 tools/brick_profile.py 99999 20 > $out/profile_w8.txt 2>&1; grep -v "Warn\|warn\|\*\*\*\|OMP" $out/profile_w8.txt | head -20
-run 8 29542 bench.py --gpus 8 --steps 50 --atoms 1000000 --no-cpu-baseline > $out/bench_1m_n8.json 2> $out/bench_1m_n8.err
-python - <<PY
-import json
-try:
-    d=json.loads([l for l in open('$out/bench_1m_n8.json') if l.startswith('{')][-1])
-    print('1M N=8', '%.4g'%d['value'], '%.4f ms'%d['ms_per_step'], 'parity', d['parity']['ok'], d['parity']['max_err_over_tol'])
-except Exception as e: print('1M failed', e)
-PY
-tail -3 $out/bench_1m_n8.err
