@@ -606,7 +606,8 @@ constexpr int kNU2 = PANTEA_NU2;
 template <int ZM1>
 __device__ __forceinline__ void angular2(const unsigned char* __restrict__ snb, const int32_t* __restrict__ list, int n_iter,
                                          double neta, double lam, double zl, int zm1_rt, double rc, int lane, int* stage,
-                                         const double* __restrict__ etab, double& oG, double& oX, double& oY, double& oZ) {
+                                         const double* __restrict__ etab, bool first_staged, double& oG, double& oX, double& oY,
+                                         double& oZ) {
     constexpr int NU = kNU2;
     const double m2_inv_rc = -2.0 / rc;
     double aG[NU], aX[NU], aY[NU], aZ[NU];
@@ -622,7 +623,7 @@ __device__ __forceinline__ void angular2(const unsigned char* __restrict__ snb, 
         for (int q = 0; q < CH / 4; ++q) cp_async16(dst + 128 * q + 4 * lane, src + 128 * q + 4 * lane);
         cp_async_commit();
     };
-    if (n_chunks > 0) stage_chunk(0);
+    if (n_chunks > 0 && !first_staged) stage_chunk(0);  // first_staged: the caller issued chunk 0 before its record arithmetic
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
         if (chunk + 1 < n_chunks) {
             stage_chunk(chunk + 1);
@@ -710,6 +711,9 @@ __device__ __forceinline__ void eval2_atom(const AtomArgs<double>& a, int w, int
     sg.load(a.tcount + (size_t)slot * kBuckets, cap);
     const int total = sg.total;
     if (sg.seg[kBuckets] > cap && lane == 0) atomicMax(&a.flags[1], sg.seg[kBuckets]);
+    const int32_t* offs = a.pair_off + (size_t)w * (a.max_groups + 1);
+    const int32_t* lists = a.pairs + (size_t)w * a.pair_cap;
+    const int off0 = tab.n_groups > 0 ? offs[0] : 0, off1 = tab.n_groups > 0 ? offs[1] : 0;  // in flight behind the index loads
 
     // ---- stage the neighbour block --------------------------------------------------------------------------------
     {
@@ -743,11 +747,16 @@ __device__ __forceinline__ void eval2_atom(const AtomArgs<double>& a, int w, int
                 }
             }
         }
-        // phase 2 (arithmetic): every lane turns its own parked vectors into records
-        for (int n = lane; n < total; n += 32) {
-            double* p = (double*)(snb + (size_t)n * kRec2Bytes);
-            const double dx = p[0], dy = p[1], dz = p[2];
-            const int ntype = __double2loint(p[3]);
+        // the first chunk of the first angular group's pair list streams into the ring while the records are computed
+        if (off1 - off0 >= 32) {
+            const int32_t* src = lists + off0;
+#pragma unroll
+            for (int q = 0; q < kChunk2 / 4; ++q) cp_async16(stage + 128 * q + 4 * lane, src + 128 * q + 4 * lane);
+            cp_async_commit();
+        }
+        // phase 2 (arithmetic): every lane turns its own parked vectors into records, two at a time (independent
+        // dependency chains: reciprocal root, two exponentials, two reciprocals each)
+        auto make_record = [&](double dx, double dy, double dz, int ntype, double (&o)[kRec2]) {
             const double r2n = dx * dx + dy * dy + dz * dz;
             const double iv = fast_rsqrt(r2n), r = r2n * iv;
             double fc, q;
@@ -765,8 +774,24 @@ __device__ __forceinline__ void eval2_atom(const AtomArgs<double>& a, int w, int
             const double eta_t = tab.v2_eta[ntype], ws_t = tab.v2_wscale[ntype];
             const double W = ws_t * fc * exp_tab256(fmax(-eta_t * r2n, -700.0), s_etab);
             const double Q = fma(-2.0 * eta_t, r, q);
-            p[0] = dx * iv; p[1] = dy * iv; p[2] = dz * iv; p[3] = r2n; p[4] = iv; p[5] = 1.4142135623730951 * r;
-            p[6] = W; p[7] = Q; p[8] = fc; p[9] = q;
+            o[0] = dx * iv; o[1] = dy * iv; o[2] = dz * iv; o[3] = r2n; o[4] = iv; o[5] = 1.4142135623730951 * r;
+            o[6] = W; o[7] = Q; o[8] = fc; o[9] = q;
+        };
+        for (int n = lane; n < total; n += 64) {
+            const bool two = n + 32 < total;
+            double* pa = (double*)(snb + (size_t)n * kRec2Bytes);
+            double* pb = (double*)(snb + (size_t)(two ? n + 32 : n) * kRec2Bytes);
+            const double ax = pa[0], ay = pa[1], az = pa[2], bx = pb[0], by = pb[1], bz = pb[2];
+            const int ta = __double2loint(pa[3]), tb = __double2loint(pb[3]);
+            double ra[kRec2], rb[kRec2];
+            make_record(ax, ay, az, ta, ra);
+            make_record(bx, by, bz, tb, rb);
+#pragma unroll
+            for (int c = 0; c < kRec2; ++c) pa[c] = ra[c];
+            if (two) {
+#pragma unroll
+                for (int c = 0; c < kRec2; ++c) pb[c] = rb[c];
+            }
         }
         // the record pad entries point at: W = 0 makes every term vanish, r^2 = 1 keeps r_jk finite
         if (lane < kRec2) ((double*)(snb + (size_t)total * kRec2Bytes))[lane] = lane == 3 ? 1.0 : 0.0;
@@ -797,19 +822,18 @@ __device__ __forceinline__ void eval2_atom(const AtomArgs<double>& a, int w, int
 
     // ---- angular symmetry functions: flat walk over the padded pair lists -------------------------------------------
     {
-        const int32_t* offs = a.pair_off + (size_t)w * (a.max_groups + 1);
-        const int32_t* lists = a.pairs + (size_t)w * a.pair_cap;
         for (int gi = 0; gi < tab.n_groups; ++gi) {
             const AngularGroup grp = tab.groups[gi];
             const AngularMember mem = tab.members[grp.first];
-            const int lo = offs[gi], n_iter = (offs[gi + 1] - lo) >> 5;
+            const int lo = gi == 0 ? off0 : offs[gi], n_iter = ((gi == 0 ? off1 : offs[gi + 1]) - lo) >> 5;
+            const bool pre = gi == 0 && off1 - off0 >= 32;  // chunk 0 is already on its way
             const double rc = tab.cls[grp.cls].rc;
             const double zl = mem.zeta * mem.lambda0;  // pref lives in the W weights
             double G, X, Y, Z;
-            if (mem.izeta == 1) angular2<0>(snb, lists + lo, n_iter, -mem.eta, mem.lambda0, zl, 0, rc, lane, stage, s_etab, G, X, Y, Z);
-            else if (mem.izeta == 2) angular2<1>(snb, lists + lo, n_iter, -mem.eta, mem.lambda0, zl, 1, rc, lane, stage, s_etab, G, X, Y, Z);
-            else if (mem.izeta == 4) angular2<3>(snb, lists + lo, n_iter, -mem.eta, mem.lambda0, zl, 3, rc, lane, stage, s_etab, G, X, Y, Z);
-            else angular2<-1>(snb, lists + lo, n_iter, -mem.eta, mem.lambda0, zl, mem.izeta - 1, rc, lane, stage, s_etab, G, X, Y, Z);
+            if (mem.izeta == 1) angular2<0>(snb, lists + lo, n_iter, -mem.eta, mem.lambda0, zl, 0, rc, lane, stage, s_etab, pre, G, X, Y, Z);
+            else if (mem.izeta == 2) angular2<1>(snb, lists + lo, n_iter, -mem.eta, mem.lambda0, zl, 1, rc, lane, stage, s_etab, pre, G, X, Y, Z);
+            else if (mem.izeta == 4) angular2<3>(snb, lists + lo, n_iter, -mem.eta, mem.lambda0, zl, 3, rc, lane, stage, s_etab, pre, G, X, Y, Z);
+            else angular2<-1>(snb, lists + lo, n_iter, -mem.eta, mem.lambda0, zl, mem.izeta - 1, rc, lane, stage, s_etab, pre, G, X, Y, Z);
             if (lane == 0) { double* o = sacc + 4 * mem.out; o[0] = G; o[1] = X; o[2] = Y; o[3] = Z; }
         }
     }
@@ -866,7 +890,7 @@ __device__ __forceinline__ float4 lds128f(const unsigned char* p) { return *rein
 template <int ZM1>
 __device__ __forceinline__ void angular2f(const unsigned char* __restrict__ snb, const int32_t* __restrict__ list, int n_iter,
                                           float neta_l2e, float lam, float zl, int zm1_rt, float rc, int lane, int* stage,
-                                          double& oG, double& oX, double& oY, double& oZ) {
+                                          bool first_staged, double& oG, double& oX, double& oY, double& oZ) {
     constexpr int NU = kNU2;
     constexpr float kL2E = 1.4426950408889634f;
     const float m2l_inv_rc = -2.0f * kL2E / rc, two_l2e = 2.0f * kL2E;
@@ -882,7 +906,7 @@ __device__ __forceinline__ void angular2f(const unsigned char* __restrict__ snb,
         for (int q = 0; q < CH / 4; ++q) cp_async16(dst + 128 * q + 4 * lane, src + 128 * q + 4 * lane);
         cp_async_commit();
     };
-    if (n_chunks > 0) stage_chunk(0);
+    if (n_chunks > 0 && !first_staged) stage_chunk(0);
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
         if (chunk + 1 < n_chunks) {
             stage_chunk(chunk + 1);
@@ -1045,10 +1069,10 @@ __device__ __forceinline__ void eval2f_atom(const AtomArgs<double>& a, int w, in
             const float rc = (float)tab.cls[grp.cls].rc;
             const float zl = (float)(mem.zeta * mem.lambda0), neta = (float)(-mem.eta) * kL2E, lam = (float)mem.lambda0;
             double G, X, Y, Z;
-            if (mem.izeta == 1) angular2f<0>(snb, lists + lo, n_iter, neta, lam, zl, 0, rc, lane, stage, G, X, Y, Z);
-            else if (mem.izeta == 2) angular2f<1>(snb, lists + lo, n_iter, neta, lam, zl, 1, rc, lane, stage, G, X, Y, Z);
-            else if (mem.izeta == 4) angular2f<3>(snb, lists + lo, n_iter, neta, lam, zl, 3, rc, lane, stage, G, X, Y, Z);
-            else angular2f<-1>(snb, lists + lo, n_iter, neta, lam, zl, mem.izeta - 1, rc, lane, stage, G, X, Y, Z);
+            if (mem.izeta == 1) angular2f<0>(snb, lists + lo, n_iter, neta, lam, zl, 0, rc, lane, stage, false, G, X, Y, Z);
+            else if (mem.izeta == 2) angular2f<1>(snb, lists + lo, n_iter, neta, lam, zl, 1, rc, lane, stage, false, G, X, Y, Z);
+            else if (mem.izeta == 4) angular2f<3>(snb, lists + lo, n_iter, neta, lam, zl, 3, rc, lane, stage, false, G, X, Y, Z);
+            else angular2f<-1>(snb, lists + lo, n_iter, neta, lam, zl, mem.izeta - 1, rc, lane, stage, false, G, X, Y, Z);
             if (lane == 0) { double* o = sacc + 4 * mem.out; o[0] = G; o[1] = X; o[2] = Y; o[3] = Z; }
         }
     }
