@@ -39,3 +39,16 @@ def test_reference_arm_ranks_above_zero_exit_without_work():
     res = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, ("--gpus", "2"))
     assert res.returncode == 0, res.stderr[-2000:]
     assert not [l for l in res.stdout.splitlines() if l.startswith("{")]
+
+
+def test_gpu_arm_refuses_to_run_without_a_gpu():
+    """The product arm has no CPU path: without a device it must stop with a message, not print a number."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    res = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                         timeout=600, cwd=str(ROOT))
+    assert res.returncode != 0
+    assert "needs a GPU" in (res.stderr + res.stdout)
+    assert not [l for l in res.stdout.splitlines() if l.startswith("{")]
