@@ -21,7 +21,10 @@ def _gpus() -> int:
 def _spawn(world: int, args, timeout=600):
     env = dict(os.environ)
     env.setdefault("PANTEA_DIST_TIMEOUT_S", "120")
-    port = 29500 + (os.getpid() % 400)
+    import socket
+    with socket.socket() as sock:  # a port that is free right now (consecutive launches do not wait out TIME_WAIT)
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(port), str(ROOT / "tests" / "mgpu_check.py"), *[str(a) for a in args]]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=str(ROOT))
