@@ -18,8 +18,9 @@
 //  * pair lists padded per group to a multiple of 32 entries with an entry that points at the all-zero record behind
 //    the last neighbour, staged 16 bytes per lane with cp.async: the loop has no bounds, validity or tail handling.
 //
-// The pair filter of this path keeps one partner per lane and accumulates a 32-bit survivor mask over a tile of 32
-// swept neighbours (9 instructions per 32 pair tests), then emits the tile's entries with one warp scan.
+// The pair filter of this path tests 32 x 32 tiles of neighbour pairs on the tensor cores (TF32 mma.sync, inclusive
+// margin; see mma_tf32_16x8x8 below), keeps a 32-bit survivor mask per lane and emits a tile's entries with one warp
+// scan, in an order that spreads the evaluation's record reads over the shared-memory banks.
 #include "acsf_common.cuh"
 
 namespace pantea {
